@@ -1,0 +1,174 @@
+"""Generate tests/golden/*.npz by running THE REFERENCE ITSELF (read-only /root/reference, `vcoder_llava`) on CPU.
+
+Only runs in the build container (the reference cannot travel to the GPU box); the fixtures it writes are
+committed.  What is executed is the reference's own code path:
+    CLIPVisionTower.forward            (vcoder_llava/model/multimodal_encoder/clip_encoder.py:39-51)
+    encode_images/seg_images/depth_images + prepare_inputs_labels_for_multimodal
+                                       (vcoder_llava/model/vcoder_ds_llava_arch.py:106-314, vcoder_llava_arch.py:131-296)
+    VCoder{,DS}LlavaLlamaForCausalLM.forward / generate
+                                       (language_model/vcoder_ds_llava_llama.py:57-142, vcoder_llava_llama.py:56-139)
+on top of the installed transformers (5.5.0; the reference pins 4.31.0 — see SURVEY.md §8c for the deltas), with
+the seeded synthetic weights of vcoder_b200.synth loaded through load_state_dict.
+
+Greedy ids are produced by BOTH working routes of SURVEY §8(c) and asserted identical:
+  (i)  model.generate(..., use_cache=False, do_sample=False)  — the reference forward+splice every step
+  (ii) prepare_inputs_labels_for_multimodal -> model.model(inputs_embeds, use_cache=True) -> lm_head -> argmax loop
+
+usage: PYTHONPATH=/root/reference python tools/make_golden.py
+"""
+import os
+import sys
+import tempfile
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+os.environ.setdefault("PYTHONDONTWRITEBYTECODE", "1")
+sys.dont_write_bytecode = True
+
+from transformers import AutoConfig, AutoModelForCausalLM  # noqa: E402
+
+# -- compatibility shim: 'llava' model_type clashes with transformers>=4.36 -------------
+_o1 = AutoConfig.register
+AutoConfig.register = staticmethod(lambda mt, cfg, exist_ok=False: _o1(mt, cfg, exist_ok=True))
+_o2 = AutoModelForCausalLM.register
+AutoModelForCausalLM.register = classmethod(lambda cls, cc, mc, exist_ok=False: _o2(cc, mc, exist_ok=True))
+
+from transformers import CLIPImageProcessor, CLIPVisionConfig, CLIPVisionModel  # noqa: E402
+
+from vcoder_llava.model import (VCoderDSLlavaLlamaForCausalLM, VCoderLlavaLlamaForCausalLM)  # noqa: E402
+from vcoder_llava.model.language_model.vcoder_ds_llava_llama import VCoderDSLlavaConfig  # noqa: E402
+from vcoder_llava.model.language_model.vcoder_llava_llama import VCoderLlavaConfig  # noqa: E402
+from vcoder_llava import mm_utils  # noqa: E402
+
+from vcoder_b200 import synth  # noqa: E402
+
+
+def build_reference_model(g, sd, tower_dir):
+    vcfg = CLIPVisionConfig(hidden_size=g.vit_hidden, intermediate_size=g.vit_ffn, num_hidden_layers=g.vit_layers,
+                            num_attention_heads=g.vit_heads, image_size=g.vit_image_size, patch_size=g.vit_patch,
+                            hidden_act="quick_gelu", layer_norm_eps=g.vit_ln_eps, projection_dim=64)
+    vcfg._attn_implementation = "eager"
+    CLIPVisionModel(vcfg).save_pretrained(tower_dir)
+    CLIPImageProcessor(size={"shortest_edge": g.vit_image_size}, crop_size=g.vit_image_size).save_pretrained(tower_dir)
+    kw = dict(hidden_size=g.llm_hidden, intermediate_size=g.llm_ffn, num_hidden_layers=g.llm_layers,
+              num_attention_heads=g.llm_heads, num_key_value_heads=g.llm_heads, vocab_size=g.llm_vocab,
+              rms_norm_eps=g.llm_rms_eps, max_position_embeddings=4096, pad_token_id=0, bos_token_id=1, eos_token_id=2,
+              mm_vision_tower=tower_dir, mm_vision_select_layer=g.vit_select_layer, mm_vision_select_feature="patch",
+              mm_projector_type="mlp2x_gelu", mm_hidden_size=g.vit_hidden, seg_mm_projector_type="mlp2x_gelu",
+              seg_mm_hidden_size=g.vit_hidden, mm_vcoder_lm_emb=True, use_mm2_proj=True, attn_implementation="eager")
+    if g.variant == synth.VARIANT_VCODER_DS:
+        cfg = VCoderDSLlavaConfig(depth_mm_projector_type="mlp2x_gelu", depth_mm_hidden_size=g.vit_hidden, **kw)
+        model = VCoderDSLlavaLlamaForCausalLM(cfg)
+    else:
+        cfg = VCoderLlavaConfig(**kw)
+        model = VCoderLlavaLlamaForCausalLM(cfg)
+    model = model.eval()
+    model.get_vision_tower().load_model()
+    model.get_vision_tower().vision_tower.config._attn_implementation = "eager"
+    # fp32 copies of the fp16-valued synthetic weights
+    ref_keys = set(model.state_dict().keys())
+    mine = {k: v.float() for k, v in sd.items()}
+    missing = sorted(k for k in ref_keys if k not in mine and "position_ids" not in k and "inv_freq" not in k)
+    extra = sorted(k for k in mine if k not in ref_keys)
+    assert not missing, f"synth.weight_specs misses reference keys: {missing[:8]}"
+    assert not extra, f"synth.weight_specs has non-reference keys: {extra[:8]}"
+    model.load_state_dict(mine, strict=False)
+    return model.float()
+
+
+@torch.no_grad()
+def run_variant(g, out_path, batch=2, n_new=6, seed=0):
+    sd = synth.make_state_dict(g, seed=seed)
+    with tempfile.TemporaryDirectory() as td:
+        model = build_reference_model(g, sd, td)
+        ids = synth.make_prompt_ids(g, batch, seed=seed, n_before=5, n_after=4)
+        images = synth.make_pixels(g, batch, 1).float()
+        segs = synth.make_pixels(g, batch, 2).float()
+        depths = synth.make_pixels(g, batch, 3).float() if g.variant == synth.VARIANT_VCODER_DS else None
+        tower = model.get_vision_tower()
+        out = {"ids": ids.numpy(), "weights_digest": np.array(synth.state_dict_digest(sd))}
+        # a1: tower + all hidden states of the first image batch
+        hs = tower.vision_tower(images, output_hidden_states=True).hidden_states
+        out["tower_hidden_states"] = torch.stack([h for h in hs]).numpy()  # [L+1, B, 1+P, D]
+        out["tower_features"] = tower(images).numpy()
+        # a2/a3
+        out["image_features"] = model.encode_images(images).numpy()
+        out["seg_features"] = model.encode_seg_images(segs).numpy()
+        if depths is not None:
+            out["depth_features"] = model.encode_depth_images(depths).numpy()
+        # a4: splice
+        mask = torch.ones_like(ids)
+        if depths is not None:
+            _, m2, _, embeds, _ = model.prepare_inputs_labels_for_multimodal(ids, mask, None, None, images, segs, depths)
+        else:
+            _, m2, _, embeds, _ = model.prepare_inputs_labels_for_multimodal(ids, mask, None, None, images, segs)
+        out["inputs_embeds"] = embeds.numpy()
+        out["spliced_mask"] = m2.numpy()
+        # a5/a6 route (i) FIRST: the reference generate() path (forward + splice each step, no cache).
+        # (Calling HF's model.model(..., output_hidden_states=True) beforehand perturbs later generate() calls under
+        #  transformers 5.5.0, so per-layer hidden states below are captured with plain forward hooks instead.)
+        kw = dict(images=images, segs=segs, do_sample=False, use_cache=False, max_new_tokens=n_new,
+                  pad_token_id=0, eos_token_id=None)
+        if depths is not None:
+            kw["depths"] = depths
+        gen = model.generate(ids, **kw)
+        gen_new = gen[:, ids.shape[1]:]
+        out["generate_ids"] = gen_new.numpy()
+        # route (ii): manual greedy loop with KV cache
+        layer_out = []
+        hooks = [l.register_forward_hook(lambda m, i, o: layer_out.append((o[0] if isinstance(o, tuple) else o).detach().clone()))
+                 for l in model.model.layers]
+        o = model.model(inputs_embeds=embeds, use_cache=True)
+        for h in hooks:
+            h.remove()
+        out["prefill_layer_outputs"] = torch.stack(layer_out).numpy()  # [L, B, T', H] residual stream after each layer
+        logits = model.lm_head(o.last_hidden_state)
+        out["prefill_logits"] = logits.numpy()
+        past = o.past_key_values
+        new_ids, step_logits = [], [logits[:, -1].numpy()]
+        nxt = logits[:, -1].argmax(-1)
+        new_ids.append(nxt)
+        for _ in range(n_new - 1):
+            o = model.model(input_ids=nxt[:, None], past_key_values=past, use_cache=True)
+            past = o.past_key_values
+            lg = model.lm_head(o.last_hidden_state)[:, -1]
+            step_logits.append(lg.numpy())
+            nxt = lg.argmax(-1)
+            new_ids.append(nxt)
+        new_ids = torch.stack(new_ids, dim=1)
+        out["greedy_ids"] = new_ids.numpy()
+        out["step_logits"] = np.stack(step_logits)  # [N, B, V]
+        assert torch.equal(gen_new, new_ids), (gen_new, new_ids)
+        np.savez_compressed(out_path, **out)
+        print(out_path, {k: getattr(v, "shape", None) for k, v in out.items()})
+        print("  greedy:", new_ids.tolist())
+
+
+def tokenizer_order_fixture(out_path):
+    """F5 known-answer: special-token order emitted by the reference tokenizer helpers (mm_utils.py:43-117)."""
+    class Tok:
+        bos_token_id = 1
+
+        def __call__(self, text):
+            return types.SimpleNamespace(input_ids=[1] + [10 + (ord(c) % 50) for c in text])
+
+    tok = Tok()
+    prompt = "<depth>\n<seg>\n<image>\nhi"
+    ds = mm_utils.tokenizer_depth_seg_token(prompt, tok, return_tensors=None)
+    sg = mm_utils.tokenizer_seg_token("<seg>\n<image>\nhi", tok, return_tensors=None)
+    np.savez_compressed(out_path, depth_seg_ids=np.array(ds), seg_ids=np.array(sg))
+    print(out_path, ds, sg)
+
+
+if __name__ == "__main__":
+    gold = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(gold, exist_ok=True)
+    torch.manual_seed(0)
+    run_variant(synth.PRESETS["tiny"].with_variant(synth.VARIANT_VCODER_DS), os.path.join(gold, "tiny_ds.npz"))
+    run_variant(synth.PRESETS["tiny"].with_variant(synth.VARIANT_VCODER), os.path.join(gold, "tiny_vcoder.npz"))
+    tokenizer_order_fixture(os.path.join(gold, "tokenizer_order.npz"))

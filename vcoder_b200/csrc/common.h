@@ -1,0 +1,78 @@
+// Shared host-side declarations for libvcoder_b200: error codes, launch-check macros and the
+// internal (C++) kernel launcher signatures. The public C ABI lives in include/vcoder_b200.h.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace vcb {
+
+// Error codes mirrored in include/vcoder_b200.h
+enum : int {
+  kOk = 0,
+  kErrInvalid = -1,       // bad argument / shape
+  kErrCuda = -2,          // CUDA runtime / driver failure (message has details)
+  kErrState = -3,         // call order (e.g. decode before prefill)
+  kErrNoMem = -4,         // KV pages / workspace exhausted
+  kErrRagged = -5,        // batch whose spliced lengths differ (the reference raises NameError there)
+  kErrSpecialIndex = -6,  // negative special id would reach the embedding table (reference: IndexError)
+  kErrNoDevice = -7,      // no CUDA device: there is deliberately NO CPU fallback
+};
+
+void set_thread_error(const std::string& msg);
+const char* get_thread_error();
+
+#define VCB_CUDA(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess) {                                                                             \
+      ::vcb::set_thread_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                       \
+      return ::vcb::kErrCuda;                                                                            \
+    }                                                                                                    \
+  } while (0)
+
+#define VCB_CHECK(cond, code, msg)                                                                       \
+  do {                                                                                                   \
+    if (!(cond)) {                                                                                       \
+      ::vcb::set_thread_error(std::string(msg) + " [" #cond "]");                                        \
+      return (code);                                                                                     \
+    }                                                                                                    \
+  } while (0)
+
+#define VCB_TRY(expr)                                                                                    \
+  do {                                                                                                   \
+    int _r = (expr);                                                                                     \
+    if (_r != 0) return _r;                                                                              \
+  } while (0)
+
+// -------------------------------------------------------------------------------------------------
+// GEMM (tcgen05): C[M,N] = epilogue(A[M,K] * W[N,K]^T)
+// -------------------------------------------------------------------------------------------------
+enum GemmAct : int { kActNone = 0, kActQuickGelu = 1, kActGeluErf = 2, kActSwiGLU = 3 };
+
+struct GemmEpilogue {
+  __half* C = nullptr;            // output, row-major, ldc elements per row
+  int ldc = 0;
+  const __half* bias = nullptr;   // [N] or null
+  const __half* residual = nullptr;  // row-major, ldr per row, or null (may alias C)
+  int ldr = 0;
+  int act = kActNone;             // kActSwiGLU: W rows interleaved (8 gate, 8 up); output has N/2 columns
+  // Output-row remap (patch-embed writes patch p of image b to row b*(group+skip)+off+p):
+  //   out_row = m + (m / out_group) * out_skip + out_off        (out_group == 0: identity)
+  int out_group = 0, out_skip = 0, out_off = 0;
+  // Residual-row remap (position embedding is indexed by patch, not by image):
+  //   res_row = res_mod ? (m % res_mod) + res_off : out_row
+  int res_mod = 0, res_off = 0;
+};
+
+// A: [M,K] fp16 row-major (lda elements), W: [N,K] fp16 row-major (ldw elements). K % 64 == 0,
+// lda/ldw % 8 == 0, N % 16 == 0. block_n: 0 = auto, else 128 or 256.
+int gemm_f16(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
+             int block_n, cudaStream_t stream);
+
+int device_sm_count();
+
+}  // namespace vcb

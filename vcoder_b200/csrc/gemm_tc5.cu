@@ -1,0 +1,323 @@
+// tcgen05 GEMM for sm_100a:  C[M,N] = epilogue( A[M,K] · W[N,K]^T ),  fp16 in, fp32 accumulate in TMEM.
+//
+// Replaces every dense nn.Linear / Conv2d-as-GEMM on the VCoder hot path that the reference reaches through
+// HF transformers -> cuBLAS/cuDNN (SURVEY.md §2.2 K1,K3,K5,K6,K9,K12):
+//   CLIP patch-embed conv  (transformers/models/clip/modeling_clip.py:150-156 -> im2col + this kernel)
+//   CLIP q/k/v/out proj, fc1 (+quick_gelu), fc2 (+residual)          (modeling_clip.py:290-345)
+//   mm_projector / seg_mm_projector  Linear+GELU(erf)+Linear          (reference vcoder_llava/model/multimodal_projector/builder.py:33-46)
+//   LLaMA q/k/v/o proj, gate/up (+SwiGLU), down (+residual) at prefill (transformers/models/llama/modeling_llama.py:171-184,224-)
+//
+// Structure (persistent, warp-specialised, one CTA per SM, 192 threads):
+//   warp 0 / lane 0 : TMA producer  — cp.async.bulk.tensor 128B-swizzled K-major tiles of A (128x64) and W (BNx64)
+//   warp 1 / lane 0 : MMA issuer    — 4 x tcgen05.mma (128 x BN x 16) per k-block, accumulators double-buffered in TMEM
+//   warps 2..5      : epilogue      — tcgen05.ld TMEM -> registers, bias / activation / residual, fp16 stores
+// Three mbarrier pipelines: smem full/empty (TMA<->MMA), TMEM full/empty (MMA<->epilogue), static tile round-robin.
+#include <algorithm>
+#include <mutex>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vcb {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 fp16 = 128 bytes = one swizzle-128B row
+constexpr int kGemmThreads = 192;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarBytes = 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +1024: manual 1 KiB alignment
+  static constexpr int kTmemCols = 2 * BN;                                     // two accumulator buffers
+};
+
+__device__ __forceinline__ float act_quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
+__device__ __forceinline__ float act_gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float act_silu(float x) { return x / (1.0f + __expf(-x)); }
+
+__device__ __forceinline__ void add_half8(float* v, const uint4& h) {
+  float2 a = unpack_half2(h.x), b = unpack_half2(h.y), c = unpack_half2(h.z), d = unpack_half2(h.w);
+  v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y; v[4] += c.x; v[5] += c.y; v[6] += d.x; v[7] += d.y;
+}
+
+template <int BN, int ACT>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmEpilogue ep,
+                int M, int N, int K, int tiles_m, int tiles_n) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (tiles_addr - raw_addr);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  const uint32_t bars_addr = tiles_addr + Cfg::kStages * Cfg::kStageBytes;
+  // barrier index map: [0,S) full, [S,2S) empty, 2S+{0,1} tmem_full, 2S+{2,3} tmem_empty
+  auto bar = [&](int i) -> uint32_t { return bars_addr + 8u * static_cast<uint32_t>(i); };
+  constexpr int S = Cfg::kStages;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * S + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2 * S; ++i) mbar_init(bar(i), 1);
+    mbar_init(bar(2 * S + 0), 1);
+    mbar_init(bar(2 * S + 1), 1);
+    mbar_init(bar(2 * S + 2), 4);
+    mbar_init(bar(2 * S + 3), 4);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_kb = K / BK;
+  const int num_tiles = tiles_m * tiles_n;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      int s = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tm = tile / tiles_n, tn = tile % tiles_n;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar(S + s), phase ^ 1u);
+          const uint32_t a_dst = tiles_addr + s * Cfg::kStageBytes;
+          mbar_expect_tx(bar(s), Cfg::kStageBytes);
+          tma_load_2d(a_dst, &tmA, bar(s), kb * BK, tm * BM);
+          tma_load_2d(a_dst + Cfg::kABytes, &tmB, bar(s), kb * BK, tn * BN);
+          if (++s == S) { s = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BM, BN);
+      int s = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(bar(2 * S + 2 + acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar(s), phase);
+          tc_fence_after();
+          const uint32_t a_addr = tiles_addr + s * Cfg::kStageBytes;
+          const uint64_t adesc = make_sw128_kmajor_desc(a_addr);
+          const uint64_t bdesc = make_sw128_kmajor_desc(a_addr + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 fp16 = 32 bytes along K inside the 128B swizzle row: +2 in the (addr >> 4) field
+            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(bar(S + s));  // frees the smem stage once these MMAs have read it
+          if (++s == S) { s = 0; phase ^= 1u; }
+        }
+        umma_commit(bar(2 * S + acc));  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue warps 2..5
+    const int q = warp & 3;  // a warp may only touch TMEM lanes [32*(warpid%4), +32)
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int tm = tile / tiles_n, tn = tile % tiles_n;
+      mbar_wait(bar(2 * S + acc), acc_phase);
+      tc_fence_after();
+      const int m = tm * BM + q * 32 + lane;
+      const bool row_ok = m < M;
+      long out_row = m;
+      if (ep.out_group) out_row = m + static_cast<long>(m / ep.out_group) * ep.out_skip + ep.out_off;
+      const long res_row = ep.res_mod ? static_cast<long>(m % ep.res_mod) + ep.res_off : out_row;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        const int n0 = tn * BN + c;
+        if (n0 >= N) break;
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c, r);
+        tmem_ld_wait();
+        if (row_ok) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (ep.bias) {
+            const uint4* bp = reinterpret_cast<const uint4*>(ep.bias + n0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) add_half8(v + 8 * j, __ldg(bp + j));
+          }
+          if (ACT == kActQuickGelu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = act_quick_gelu(v[j]);
+          } else if (ACT == kActGeluErf) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = act_gelu_erf(v[j]);
+          }
+          if (ACT == kActSwiGLU) {
+            // columns [16g, 16g+8) = gate, [16g+8, 16g+16) = up  ->  8 outputs per granule
+            uint32_t o[8];
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+#pragma unroll
+              for (int e = 0; e < 8; e += 2) {
+                const float a = act_silu(v[16 * g + e]) * v[16 * g + 8 + e];
+                const float b = act_silu(v[16 * g + e + 1]) * v[16 * g + 8 + e + 1];
+                o[4 * g + e / 2] = pack_half2(a, b);
+              }
+            }
+            uint4* cp = reinterpret_cast<uint4*>(ep.C + out_row * ep.ldc + (n0 >> 1));
+            cp[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            cp[1] = make_uint4(o[4], o[5], o[6], o[7]);
+          } else {
+            if (ep.residual) {
+              const uint4* rp = reinterpret_cast<const uint4*>(ep.residual + res_row * ep.ldr + n0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) add_half8(v + 8 * j, rp[j]);
+            }
+            uint4* cp = reinterpret_cast<uint4*>(ep.C + out_row * ep.ldc + n0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              cp[j] = make_uint4(pack_half2(v[8 * j + 0], v[8 * j + 1]), pack_half2(v[8 * j + 2], v[8 * j + 3]),
+                                 pack_half2(v[8 * j + 4], v[8 * j + 5]), pack_half2(v[8 * j + 6], v[8 * j + 7]));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(2 * S + 2 + acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+  });
+  return fn;
+}
+
+int make_tmap_kmajor(CUtensorMap* m, const void* ptr, uint64_t k, uint64_t rows, uint64_t ld_elems,
+                     uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  VCB_CHECK(fn != nullptr, kErrCuda, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {k, rows};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_thread_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
+    return kErrCuda;
+  }
+  return kOk;
+}
+
+template <int BN, int ACT>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpilogue& ep, int M, int N, int K,
+           cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VCB_CUDA(cudaFuncSetAttribute(gemm_tc5_kernel<BN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles_m = (M + BM - 1) / BM;
+  const int tiles_n = (N + BN - 1) / BN;
+  const int grid = std::min(tiles_m * tiles_n, device_sm_count());
+  gemm_tc5_kernel<BN, ACT><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, ep, M, N, K, tiles_m, tiles_n);
+  VCB_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+template <int BN>
+int launch_act(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpilogue& ep, int M, int N, int K,
+               cudaStream_t stream) {
+  switch (ep.act) {
+    case kActNone: return launch<BN, kActNone>(tmA, tmB, ep, M, N, K, stream);
+    case kActQuickGelu: return launch<BN, kActQuickGelu>(tmA, tmB, ep, M, N, K, stream);
+    case kActGeluErf: return launch<BN, kActGeluErf>(tmA, tmB, ep, M, N, K, stream);
+    case kActSwiGLU: return launch<BN, kActSwiGLU>(tmA, tmB, ep, M, N, K, stream);
+    default: set_thread_error("gemm_f16: unknown activation"); return kErrInvalid;
+  }
+}
+
+}  // namespace
+
+int device_sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        n <= 0) {
+      n = 148;
+    }
+  }
+  return n;
+}
+
+int gemm_f16(const __half* A, int lda, const __half* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
+             int block_n, cudaStream_t stream) {
+  VCB_CHECK(M > 0 && N > 0 && K > 0, kErrInvalid, "gemm_f16: empty problem");
+  VCB_CHECK(K % BK == 0, kErrInvalid, "gemm_f16: K must be a multiple of 64");
+  VCB_CHECK(N % 32 == 0, kErrInvalid, "gemm_f16: N must be a multiple of 32");
+  VCB_CHECK(lda % 8 == 0 && ldw % 8 == 0, kErrInvalid, "gemm_f16: leading dimensions must be multiples of 8");
+  VCB_CHECK((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(ep.C) & 15) == 0,
+            kErrInvalid, "gemm_f16: pointers must be 16-byte aligned");
+  VCB_CHECK(ep.C != nullptr && ep.ldc % 8 == 0, kErrInvalid, "gemm_f16: bad output");
+  int bn = block_n;
+  if (bn == 0) {
+    // 256-wide tiles halve the A re-reads; keep 128 when that would leave SMs idle.
+    const long tiles256 = static_cast<long>((M + BM - 1) / BM) * ((N + 255) / 256);
+    bn = (N % 256 == 0 && tiles256 >= device_sm_count()) ? 256 : 128;
+  }
+  VCB_CHECK(bn == 128 || bn == 256, kErrInvalid, "gemm_f16: block_n must be 0, 128 or 256");
+  CUtensorMap tmA, tmB;
+  VCB_TRY(make_tmap_kmajor(&tmA, A, K, M, lda, BM));
+  VCB_TRY(make_tmap_kmajor(&tmB, W, K, N, ldw, bn));
+  return bn == 256 ? launch_act<256>(tmA, tmB, ep, M, N, K, stream) : launch_act<128>(tmA, tmB, ep, M, N, K, stream);
+}
+
+}  // namespace vcb
