@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py — end-to-end tokens/sec (prefill + decode) of VCoder-DS LLaVA-1.5-7B, batch 8 per GPU, 128 new tokens,
+greedy, synthetic 336x336 images and seeded random-init weights (BASELINE.json configs[2]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One "step" = one full generate job over one batch: 3x8 images through the shared CLIP ViT-L/14@336 tower,
+projectors, splice, 32-layer prefill over T' = 1208 tokens and 127 greedy decode steps.
+  value : tokens/s with pixels already resident in HBM (prefill + decode launched through the C ABI)
+  e2e   : tokens/s through the reference-facing call (`Engine.generate` -> vcb_generate) with HOST buffers: pinned
+          pixels/ids copied H2D and the generated ids copied D2H inside the timed region
+  --impl reference : the oracle port of the reference's CPU path (fp32 torch-on-CPU, all host threads), timed on a
+          bounded sample of the same workload and scaled to tokens/s (the full job is ~10 minutes of CPU).
+N > 1 (torchrun): every rank runs its own replica on its own batch of 8 (weak scaling); the generated ids are joined
+with ONE NCCL all-gather inside the timed region; time = max over ranks (CUDA events).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        sm.sort()
+        # median over the upper half of samples = "under load" (idle gaps between steps pull the clock down)
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": (load[len(load) // 2] if load else None), "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path, bounded sample scaled to the full job
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_sample_tokens_per_s(B, n_new, repeats=1):
+    """Times, with every host thread, one image through the ViT-L tower + projector, one LLaMA-7B layer of prefill
+    (B=1, T'=1208), one layer of a decode step (B=8, ctx ~1270) and the lm_head, then scales by the job's counts:
+      total = 3B*t_img + B*32*t_prefill_layer + (n_new-1)*(32*t_decode_layer + t_lm_head) + t_lm_head."""
+    from oracle import vcoder_oracle as orc
+    from vcoder_b200 import synth
+
+    torch.set_num_threads(os.cpu_count())
+    g = synth.PRESETS["7b"]
+    Tp = 55 + 3 - 3 + 2 * g.n_patches  # 58 ids incl. 3 specials -> 55 text + 1152 visual
+    H, dh = g.llm_hidden, 128
+    gen = torch.Generator().manual_seed(0)
+    # --- tower + projector on one image
+    sd_v = synth.make_state_dict(g, seed=0, only_prefix="model.vision_tower.")
+    sd_v.update(synth.make_state_dict(g, seed=0, only_prefix="model.mm_projector."))
+    sd_v = {k: v.float() for k, v in sd_v.items()}
+    px = synth.make_pixels(g, 1, 1).float()
+    t_img = []
+    for _ in range(1 + repeats):
+        t0 = time.perf_counter()
+        f = orc.clip_tower_forward(px, sd_v, g)
+        orc.projector(f, sd_v, "mm_projector")
+        t_img.append(time.perf_counter() - t0)
+    del sd_v
+    # --- one decoder layer
+    sd_l = {k: v.float() for k, v in synth.make_state_dict(g, seed=0, only_prefix="model.layers.0.").items()}
+    x = torch.randn(1, Tp, H, generator=gen)
+    t_pl = []
+    for _ in range(1 + repeats):
+        cache = orc.KVCache(1)
+        t0 = time.perf_counter()
+        orc.llama_layer(x, sd_l, 0, g, cache, 0)
+        t_pl.append(time.perf_counter() - t0)
+    xd = torch.randn(B, 1, H, generator=gen)
+    ctx = Tp + n_new // 2
+    t_dl = []
+    for _ in range(2 + 2 * repeats):
+        cache = orc.KVCache(1)
+        cache.k[0] = torch.randn(B, g.llm_heads, ctx, dh, generator=gen)
+        cache.v[0] = torch.randn(B, g.llm_heads, ctx, dh, generator=gen)
+        t0 = time.perf_counter()
+        orc.llama_layer(xd, sd_l, 0, g, cache, ctx)
+        t_dl.append(time.perf_counter() - t0)
+    del sd_l
+    w_lm = torch.randn(g.llm_vocab, H, generator=gen) * 0.02
+    xl = torch.randn(B, H, generator=gen)
+    t_lm = []
+    for _ in range(2 + repeats):
+        t0 = time.perf_counter()
+        torch.nn.functional.linear(xl, w_lm)
+        t_lm.append(time.perf_counter() - t0)
+    ti, tp, td, tl = min(t_img[1:]), min(t_pl[1:]), min(t_dl[1:]), min(t_lm[1:])
+    total = 3 * B * ti + B * g.llm_layers * tp + (n_new - 1) * (g.llm_layers * td + tl) + tl
+    cpu_work = sum(t_img) + sum(t_pl) + sum(t_dl) + sum(t_lm)
+    return {
+        "value": B * n_new / total, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port",
+        "sample": (f"oracle fp32 torch-CPU: 1 image ViT-L tower+projector {ti:.2f}s, 1 LLaMA-7B layer prefill B=1 T'={Tp} "
+                   f"{tp:.2f}s, 1 layer decode step B={B} ctx={ctx} {td * 1e3:.0f}ms, lm_head {tl * 1e3:.0f}ms; scaled to the "
+                   f"full job ({total:.0f}s); {cpu_work:.0f}s of CPU work sampled"),
+        "job_seconds_est": total,
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    last = None
+    for i in range(args.warmup + args.steps):
+        last = cpu_sample_tokens_per_s(args.batch, args.new_tokens, repeats=1)
+        if i >= args.warmup:
+            vals.append(last["value"])
+    v = sum(vals) / len(vals)
+    last["value"] = v
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * args.batch * args.new_tokens / v, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, 1),
+        "cpu_baseline": last, "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+METRIC = "end-to-end tokens/sec (prefill+decode) VCoder-DS-7B bs8"
+
+
+def workload_config(args, world):
+    return {"workload": f"VCoder-DS LLaVA-1.5-{args.preset.upper()}, RGB+seg+depth towers (CLIP ViT-L/14@336), batch {args.batch} "
+                        f"per GPU, prompt 58 ids -> T'=1207 spliced tokens, {args.new_tokens} new tokens, greedy (BASELINE.json configs[2])",
+            "global_batch": args.batch * world, "new_tokens": args.new_tokens, "parallelism": f"dp{world} (replicas, one NCCL all-gather of ids)",
+            "l2": "inputs larger than L2: 13.5 GB of weights + KV streamed per decode step vs 126 MB L2; no explicit flush",
+            "weights": "seeded random-init fp16 (HF std 0.02)"}
+
+
+def bind_synthetic(eng, g, seed, device):
+    """Generate each tensor on the device and bind it immediately (keeps peak memory at one tensor over the model)."""
+    from vcoder_b200 import synth
+    specs = synth.weight_specs(g)
+    for name, shape, kind, std in specs:
+        gen = torch.Generator(device=device)
+        gen.manual_seed(synth._seed_for(name, seed))
+        t = torch.randn(shape, generator=gen, device=device, dtype=torch.float32)
+        t = (1.0 + std * t) if kind == "ln_weight" else (std * t)
+        eng.bind({name: t.to(torch.float16)})
+        del t
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    from vcoder_b200 import _lib, synth
+    from vcoder_b200.engine import Engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl b200 needs a GPU: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    g = synth.PRESETS[args.preset].with_variant(synth.VARIANT_VCODER_DS)
+    B, N = args.batch, args.new_tokens
+    ids = synth.make_prompt_ids(g, B, seed=rank)  # [B, 58]
+    Tp = ids.shape[1] - 3 + 2 * g.n_patches
+    eng = Engine(g, max_batch=B, max_seq_len=((Tp + N + 63) // 64) * 64, device=local)
+    bind_synthetic(eng, g, seed=0, device=dev)
+    torch.cuda.synchronize()
+    host_px = [synth.make_pixels(g, B, 10 * rank + s).pin_memory() for s in (1, 2, 3)]
+    ids_pinned = ids.pin_memory()
+    dev_px = [p.to(dev) for p in host_px]
+    gathered = torch.empty(world * B, N, dtype=torch.int32, device=dev) if world > 1 else None
+    stream = torch.cuda.current_stream()
+
+    def step_resident():
+        pre = eng.prefill(ids, dev_px[0], dev_px[1], dev_px[2])
+        dec = eng.decode(N - 1)
+        out = torch.cat([pre["next_ids"][:, None], dec], dim=1)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)  # K14: the only collective on the path
+        return out
+
+    def step_e2e():
+        out = eng.generate(ids_pinned, host_px[0], host_px[1], host_px[2], max_new_tokens=N)  # host in, host out
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out.to(dev, torch.int32))
+        return out
+
+    def timed(fn, k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0 = lib.vcb_launch_count()
+        e0.record(stream)
+        for _ in range(k):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        launches = lib.vcb_launch_count() - c0
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches
+
+    for _ in range(args.warmup):
+        step_resident()
+        step_e2e()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_res, launches = timed(step_resident, args.steps)
+    ms_e2e, _ = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    tokens = world * B * N * args.steps
+    value = tokens / (ms_res / 1e3)
+    e2e_value = tokens / (ms_e2e / 1e3)
+
+    # ---- live per-kernel timing of one more step (CUDA events around every launch, graph disabled)
+    roofline, breakdown = None, None
+    if rank == 0:
+        import ctypes as C
+        peaks = load_peaks()
+        lib.vcb_profile_enable(1)
+        step_resident()
+        ms = (C.c_float * 8)()
+        nl = (C.c_uint64 * 8)()
+        _lib.check(lib.vcb_profile_read(ms, nl, 8))
+        lib.vcb_profile_enable(0)
+        breakdown = {c: {"ms": round(float(ms[i]), 3), "launches": int(nl[i])} for i, c in enumerate(_lib.PROFILE_CATEGORIES)}
+        tot = sum(v["ms"] for v in breakdown.values())
+        for v in breakdown.values():
+            v["share"] = round(v["ms"] / tot, 4) if tot else None
+        # dominant kernel: the decode weight-streaming skinny GEMM (HBM-bound).  Algorithmic bytes per launch =
+        # the weight matrix it streams once: per decode step 32 x (qkv 3H*H + o H*H + gate|up 2F*H + down H*F) + lm_head
+        H, F, V, L = g.llm_hidden, g.llm_ffn, g.llm_vocab, g.llm_layers
+        step_bytes = 2 * (L * (3 * H * H + H * H + 2 * F * H + H * F) + V * H)
+        sk = breakdown["skinny_gemm"]
+        total_bytes = step_bytes * (N - 1) + 2 * V * H  # + the prefill's last-position lm_head
+        ach = total_bytes / (sk["ms"] / 1e3) / 1e9 if sk["ms"] else None
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "skinny_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        roofline = {"kernel": "skinny_gemm_kernel (decode weight streaming: qkv/o/gate-up/down/lm_head)", "bound": "hbm",
+                    "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": (ach / peaks["hbm_gbs"]) if ach else None,
+                    "traffic": traffic, "peak_source": peaks["source"],
+                    "bytes_per_launch_avg": total_bytes / max(1, sk["launches"]), "launches": sk["launches"],
+                    "note": "CUDA events bracket each launch (~2 us event overhead included)"}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_sample_tokens_per_s(B, N, repeats=1)
+    if rank == 0:
+        h2d = sum(p.numel() * 2 for p in host_px) + ids.numel() * 8
+        line = {
+            "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16", "data": "synthetic", "config": workload_config(args, world),
+            "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * N * 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernel_breakdown": breakdown,
+            "cpu_baseline": cpu, "impl": "b200",
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--preset", default="7b")
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--new-tokens", type=int, default=128)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -100,6 +100,92 @@ int vcb_op_gemm_f16(const vcb_half* A_dev, int32_t lda, const vcb_half* W_dev, i
                     int32_t K, const vcb_half* bias_dev, const vcb_half* residual_dev, int32_t ldr, int32_t act,
                     vcb_half* C_dev, int32_t ldc, int32_t block_n, void* stream);
 
+/* Y[B,N] = X[B,K] · W[N,K]^T (+ residual), B <= 32: the decode / lm_head weight-streaming kernel.
+ * swiglu != 0: W rows 8/8 interleaved gate|up, Y has N/2 columns. */
+int vcb_op_skinny_gemm_f16(const vcb_half* X_dev, int32_t ldx, const vcb_half* W_dev, int32_t B, int32_t N, int32_t K,
+                           const vcb_half* residual_dev, int32_t ldr, int32_t swiglu, vcb_half* Y_dev, int32_t ldy,
+                           void* stream);
+
+/* nn.LayerNorm over the last dim (CLIP pre_layrnorm / layer_norm1/2), rows x D fp16. */
+int vcb_op_layernorm_f16(const vcb_half* x_dev, const vcb_half* w_dev, const vcb_half* b_dev, vcb_half* y_dev,
+                         int64_t rows, int32_t D, float eps, void* stream);
+/* LlamaRMSNorm (transformers/models/llama/modeling_llama.py:53-70), rows x H fp16. */
+int vcb_op_rmsnorm_f16(const vcb_half* x_dev, const vcb_half* w_dev, vcb_half* y_dev, int64_t rows, int32_t H,
+                       float eps, void* stream);
+
+/* CLIP self-attention on a packed qkv buffer [B*S, 3*heads*64] -> out [B*S, heads*64];
+ * softmax(q k^T * scale) v, no mask (transformers/models/clip/modeling_clip.py:261-279). */
+int vcb_op_attention_vit_f16(const vcb_half* qkv_dev, int32_t B, int32_t S, int32_t heads, float scale,
+                             vcb_half* out_dev, void* stream);
+
+/* ---- host-only logic ------------------------------------------------------------------------ */
+
+/* The splice plan of prepare_inputs_labels_for_multimodal (vcoder_ds_llava_arch.py:175-312 /
+ * vcoder_llava_arch.py:182-294) for ids_host [B,T].  depth_nonzero_host: NULL when depths is None, else B bytes
+ * (`mean(depth) != 0`).  plan_out (capacity plan_cap int32) receives B*out_len entries:
+ *   >= 0 token id, -1 zero pad, <= -2 row -(v+2) of the feature buffer laid out [kind(rgb,seg,depth)][B][1+P] (row 0 of
+ *   each image is the CLS token and is never referenced).  Needs no GPU. */
+int vcb_splice_plan(int32_t variant, const int64_t* ids_host, int32_t B, int32_t T, int32_t n_patches, int32_t has_seg,
+                    const uint8_t* depth_nonzero_host, int32_t* plan_out, int64_t plan_cap, int32_t* out_len);
+
+/* ---- engine --------------------------------------------------------------------------------- */
+
+/* Replaces load_pretrained_model's model construction (vcoder_llava/model/builder.py:93-143): allocates packed
+ * weight storage, workspaces and the paged KV cache on `device`. */
+int vcb_create(const vcb_config* cfg, int32_t device, vcb_handle* out);
+int vcb_destroy(vcb_handle h);
+
+/* Replaces from_pretrained's state-dict load. Tensors are COPIED (and packed: q|k|v concatenated, gate/up
+ * interleaved) into handle-owned memory, so the caller may free its copies afterwards.  Unknown or dead names
+ * (depth_mm_projector.*, mm2_projector.*, vcoder_lm_emb.weight, post_layernorm.*, encoder layers past the tapped
+ * one) are accepted and ignored, as the reference never reads them at inference. */
+int vcb_bind_weights(vcb_handle h, const vcb_tensor* tensors, int32_t n);
+
+/* CLIPVisionTower.forward (clip_encoder.py:39-51): pixels_any [n,3,S,S] fp16 -> out_any [n,P,D] fp16
+ * = hidden_states[select_layer][:, 1:]. n <= 3*max_batch. */
+int vcb_tower_forward(vcb_handle h, const vcb_half* pixels_any, int32_t n, vcb_half* out_any, void* stream);
+
+/* encode_images (modality 0: mm_projector), encode_seg_images (1) / encode_depth_images (2): both seg_mm_projector
+ * (vcoder_ds_llava_arch.py:106-119).  pixels_any [n,3,S,S] -> out_any [n,P,H]. */
+int vcb_encode(vcb_handle h, int32_t modality, const vcb_half* pixels_any, int32_t n, vcb_half* out_any, void* stream);
+
+/* VCoder*LlavaLlamaForCausalLM.forward at prefill (vcoder_ds_llava_llama.py:57-118): towers + projectors + splice +
+ * decoder stack + lm_head on the last position + greedy argmax.  ids_host [B,T] int64 with the -200/-300/-400
+ * specials; images/segs/depths_any [B,3,S,S] fp16 (segs/depths may be NULL; images NULL = text-only).
+ * Optional outputs (any, may be NULL): next_ids [B] int32, last_logits [B,V] fp16, embeds [B,T',H] fp16 (the spliced
+ * inputs_embeds), spliced_len (host int32). Resets the KV cache. */
+int vcb_prefill(vcb_handle h, const int64_t* ids_host, int32_t B, int32_t T, const vcb_half* images_any,
+                const vcb_half* segs_any, const vcb_half* depths_any, int32_t* next_ids_any, vcb_half* last_logits_any,
+                vcb_half* embeds_any, int32_t* spliced_len_host, void* stream);
+
+/* n_steps greedy decode steps (prepare_inputs_for_generation + forward + argmax, vcoder_ds_llava_llama.py:120-142;
+ * every cached position is attended, padding included: vcoder_ds_llava_arch.py:130-133).  out_ids_any [B,n_steps]
+ * int32 receives the tokens produced by THIS call; logits_trace_any [n_steps,B,V] fp16 optional (disables the CUDA
+ * graph).  Asynchronous on `stream` unless an output is pageable host memory. */
+int vcb_decode(vcb_handle h, int32_t n_steps, int32_t* out_ids_any, vcb_half* logits_trace_any, void* stream);
+
+/* model.generate(input_ids, images=, segs=, depths=, do_sample=False, max_new_tokens=N) for HOST buffers: prefill +
+ * N-1 decode steps, copies the N new ids per sequence to out_ids_host [B,N] int64 and synchronises.  This is the
+ * end-to-end entry the callers (serve/cli.py:121-132, eval/model_depth_loader.py:146-168) map onto. */
+int vcb_generate(vcb_handle h, const int64_t* ids_host, int32_t B, int32_t T, const vcb_half* images_any,
+                 const vcb_half* segs_any, const vcb_half* depths_any, int32_t max_new_tokens, int64_t* out_ids_host,
+                 void* stream);
+
+/* Drops the KV cache contents (pages return to the pool). */
+int vcb_reset(vcb_handle h);
+
+/* ---- accounting (bench.py: `gpu_launches`, live per-kernel timings for the roofline) ------------------ */
+
+/* Kernels launched by this library in this process so far (graph replays count their kernel nodes). */
+uint64_t vcb_launch_count(void);
+
+/* Per-category CUDA-event timing of every launch (disables the decode CUDA graph while on).
+ * Categories: 0 tcgen05 GEMM, 1 skinny GEMM, 2 ViT attention, 3 LLaMA prefill attention, 4 decode attention,
+ * 5 LayerNorm/RMSNorm, 6 RoPE + KV append, 7 gather/argmax/misc. */
+#define VCB_PROFILE_CATEGORIES 8
+int vcb_profile_enable(int32_t on);
+int vcb_profile_read(float* ms_by_category, uint64_t* launches_by_category, int32_t n_categories);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,147 @@
+"""CPU-side checks of the C ABI: the library loads, exports every symbol include/vcoder_b200.h declares, refuses to
+compute without a GPU (no CPU fallback), and its host-only splice planner agrees with the oracle's restatement of
+prepare_inputs_labels_for_multimodal (which tests/test_oracle_golden.py pins to the reference)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vcoder_oracle as orc
+from vcoder_b200 import _lib, synth
+from vcoder_b200.engine import splice_plan
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+I, S, D = synth.IMAGE_TOKEN_INDEX, synth.SEG_TOKEN_INDEX, synth.DEPTH_TOKEN_INDEX
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "vcoder_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vcb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/vcoder_b200.h but not exported"
+    assert sorted(_lib.SIGNATURES) == declared, "python binding and header disagree"
+    assert b"sm_100a" in lib.vcb_version()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    lib = _lib.load()
+    assert lib.vcb_device_count() == 0
+    cfg = _lib.VcbConfig(struct_size=C.sizeof(_lib.VcbConfig))
+    h = C.c_void_p()
+    assert lib.vcb_create(C.byref(cfg), 0, C.byref(h)) == -7  # VCB_ERR_NO_DEVICE
+    assert b"no CPU fallback" in lib.vcb_last_error()
+    x = np.zeros((8, 64), dtype=np.float16)
+    rc = lib.vcb_op_gemm_f16(_lib.ptr(x), 64, _lib.ptr(x), 64, 8, 8, 64, None, None, 0, 0, _lib.ptr(x), 64, 0, None)
+    assert rc == -7
+    from vcoder_b200.engine import Engine
+    with pytest.raises(RuntimeError):
+        Engine(synth.PRESETS["tiny"])
+
+
+def _oracle_plan_rows(ids, ds, has_seg, nz, P, B):
+    """Expand the oracle's segment plan to the flat row encoding of vcb_splice_plan."""
+    plans = orc.splice_plan(ids, ds, has_seg, nz)
+    kind = {"image": 0, "seg": 1, "depth": 2}
+    rows = []
+    for segs in plans:
+        r = []
+        for k, payload in segs:
+            if k == "text":
+                r += list(payload)
+            else:
+                base = (kind[k] * B + payload) * (P + 1) + 1
+                r += [-(base + p) - 2 for p in range(P)]
+        rows.append(r)
+    return rows
+
+
+CASES = [
+    # (variant_ds, ids, has_seg, depth_nonzero)
+    (True, [[1, 5, I, D, S, 9], [1, 6, I, D, S, 7]], True, [True, True]),   # reference tokenizer order (F5)
+    (True, [[1, I, 7, S, 8, D, 9]], True, [True]),                          # depth after seg: spliced
+    (True, [[1, I, 9, 4]], True, [True]),                                   # DS tolerates image-only
+    (True, [[1, 2, 3, 4, 5]], True, None),                                  # text only
+    (False, [[1, I, 7, S, 9], [2, I, 8, S, 3]], True, None),                # VCoder keeps text between
+    (True, [[1, I, S, 4, I, 5]], True, [True]),                             # second image after seg is never consumed? (error)
+    (True, [[I, S, D]], True, [True]),
+]
+
+
+@pytest.mark.parametrize("ds,ids,has_seg,nz", CASES)
+def test_splice_plan_matches_oracle(ds, ids, has_seg, nz):
+    P = 4
+    B = len(ids)
+    variant = synth.VARIANT_VCODER_DS if ds else synth.VARIANT_VCODER
+    try:
+        want = _oracle_plan_rows(ids, ds, has_seg, nz, P, B)
+        want_err = None
+    except orc.SpliceError as e:
+        want, want_err = None, e
+    if want is not None and len({len(r) for r in want}) > 1:
+        want, want_err = None, "ragged"
+    try:
+        got = splice_plan(variant, ids, P, has_seg, nz)
+    except _lib.VcbError as e:
+        assert want is None, f"C planner failed ({e}) where the oracle succeeded"
+        assert e.code in (-5, -6, -1)
+        return
+    assert want is not None, f"oracle raised {want_err} but the C planner returned a plan"
+    assert got.tolist() == want
+
+
+def test_splice_plan_error_codes():
+    # VCoder with <image> but no <seg>: dummy branch feeds -200 to nn.Embedding -> IndexError (F11)
+    with pytest.raises(_lib.VcbError) as ei:
+        splice_plan(synth.VARIANT_VCODER, [[1, I, 9]], 4, True, None)
+    assert ei.value.code == -6
+    # is_depth_zero with a reachable <depth> token: the id reaches the embedding
+    with pytest.raises(_lib.VcbError) as ei:
+        splice_plan(synth.VARIANT_VCODER_DS, [[1, I, 7, S, 8, D, 9]], 4, True, [False])
+    assert ei.value.code == -6
+    # ragged batch: the reference dies with NameError (_new_labels)
+    with pytest.raises(_lib.VcbError) as ei:
+        splice_plan(synth.VARIANT_VCODER_DS, [[1, I, S, 9], [1, 5, 5, 9]], 4, True, [True, True])
+    assert ei.value.code == -5
+
+
+def test_splice_plan_random_fuzz():
+    rng = np.random.RandomState(0)
+    P = 3
+    n_ok = 0
+    for trial in range(300):
+        ds = bool(rng.randint(2))
+        B = rng.randint(1, 4)
+        T = rng.randint(3, 9)
+        ids = rng.randint(3, 50, size=(B, T)).astype(np.int64)
+        # same special layout in every row so lengths agree
+        specials = [I, S] if not ds else [[I, D, S], [I, S, D], [I, S], [I]][rng.randint(4)]
+        pos = sorted(rng.choice(np.arange(1, T), size=min(len(specials), T - 1), replace=False))
+        for b in range(B):
+            for p, s in zip(pos, specials):
+                ids[b, p] = s
+        nz = [bool(rng.randint(2)) for _ in range(B)] if ds else None
+        variant = synth.VARIANT_VCODER_DS if ds else synth.VARIANT_VCODER
+        try:
+            want = _oracle_plan_rows(ids.tolist(), ds, True, nz, P, B)
+        except orc.SpliceError:
+            want = None
+        if want is not None and len({len(r) for r in want}) > 1:
+            want = None
+        try:
+            got = splice_plan(variant, ids, P, True, nz).tolist()
+        except _lib.VcbError:
+            got = None
+        assert got == want, (ds, ids.tolist(), nz)
+        n_ok += want is not None
+    assert n_ok > 50

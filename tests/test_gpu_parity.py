@@ -1,0 +1,240 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Everything goes through the C ABI
+(libvcoder_b200.so via ctypes); the checker is the CPU oracle (fp32) and the committed golden fixtures written by the
+reference itself.  Integer work (splice plan, ids) is bit-exact; floating point is compared with the stated fp16
+tolerances:
+
+  single kernels (fp16 in/out, fp32 accumulate):  rel-RMS <= 5e-4, max-abs <= 2 fp16 ulps of the largest output
+  towers / projectors / logits (fp16 residual stream between kernels, N layers deep): rel-RMS <= 4e-3
+  greedy ids: equal to the oracle's wherever the oracle's top-1/top-2 logit margin exceeds 2x the measured logit
+              error (near-ties below the fp16 noise floor are not decidable by ANY fp16 implementation).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vcoder_oracle as orc
+from vcoder_b200 import _lib, synth
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from vcoder_b200.engine import Engine
+
+DEV = "cuda"
+ST = C.c_void_p(0)
+
+
+def rel_rms(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return float((a - b).pow(2).mean().sqrt() / (b.pow(2).mean().sqrt() + 1e-12))
+
+
+def max_abs(a, b):
+    return float((a.float().cpu() - b.float().cpu()).abs().max())
+
+
+def ulp16(x):
+    """fp16 spacing at magnitude x."""
+    return float(2.0 ** (np.floor(np.log2(max(abs(x), 6e-5))) - 10))
+
+
+def assert_close_kernel(got, ref, what):
+    r = rel_rms(got, ref)
+    m = max_abs(got, ref)
+    amax = float(ref.float().abs().max())
+    assert not torch.isnan(got.float()).any(), what
+    assert r <= 5e-4, f"{what}: rel-rms {r}"
+    assert m <= 2.5 * ulp16(amax), f"{what}: max-abs {m} vs ulp {ulp16(amax)}"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# operator level
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K,act,bias,res,bn", [
+    (128, 128, 64, 0, 0, 0, 128), (300, 384, 640, 0, 1, 0, 128), (300, 512, 640, 1, 1, 1, 256),
+    (1000, 1024, 1024, 2, 1, 0, 0), (1000, 1024, 1024, 3, 0, 0, 128), (577 * 3, 3072, 1024, 0, 1, 0, 0),
+    (1, 256, 128, 0, 1, 1, 128), (2 * 1207, 4096, 4096, 0, 0, 1, 256),
+])
+def test_gemm_tc5(M, N, K, act, bias, res, bn):
+    lib = _lib.load()
+    torch.manual_seed(M + N + K)
+    A = (torch.randn(M, K, device=DEV) * 0.5).half()
+    W = (torch.randn(N, K, device=DEV) * 0.05).half()
+    b = (torch.randn(N, device=DEV) * 0.1).half() if bias else None
+    R = (torch.randn(M, N, device=DEV) * 0.5).half() if res else None
+    No = N // 2 if act == 3 else N
+    Cc = torch.full((M, No), float("nan"), device=DEV, dtype=torch.float16)
+    _lib.check(lib.vcb_op_gemm_f16(_lib.ptr(A), K, _lib.ptr(W), K, M, N, K, _lib.ptr(b), _lib.ptr(R), N, act, _lib.ptr(Cc), No, bn, ST))
+    torch.cuda.synchronize()
+    ref = A.float().cpu() @ W.float().cpu().t()
+    if b is not None:
+        ref = ref + b.float().cpu()
+    if act == 1:
+        ref = orc.quick_gelu(ref)
+    elif act == 2:
+        ref = torch.nn.functional.gelu(ref)
+    elif act == 3:
+        r = ref.view(M, N // 16, 2, 8)
+        ref = (torch.nn.functional.silu(r[:, :, 0]) * r[:, :, 1]).reshape(M, N // 2)
+    if R is not None:
+        ref = ref + R.float().cpu()
+    assert_close_kernel(Cc, ref, f"gemm {M}x{N}x{K} act{act}")
+
+
+@pytest.mark.parametrize("B,N,K,sw,res", [(8, 4096, 4096, 0, 1), (8, 1024, 512, 1, 0), (3, 512, 256, 0, 0),
+                                          (1, 32000, 4096, 0, 0), (16, 2048, 1024, 0, 1), (32, 1024, 512, 1, 0),
+                                          (8, 4096, 11008, 0, 1)])
+def test_skinny_gemm(B, N, K, sw, res):
+    lib = _lib.load()
+    torch.manual_seed(B + N)
+    X = (torch.randn(B, K, device=DEV) * 0.5).half()
+    W = (torch.randn(N, K, device=DEV) * 0.03).half()
+    R = torch.randn(B, N, device=DEV).half() if res else None
+    No = N // 2 if sw else N
+    Y = torch.full((B, No), float("nan"), device=DEV, dtype=torch.float16)
+    _lib.check(lib.vcb_op_skinny_gemm_f16(_lib.ptr(X), K, _lib.ptr(W), B, N, K, _lib.ptr(R), N, sw, _lib.ptr(Y), No, ST))
+    torch.cuda.synchronize()
+    ref = X.float().cpu() @ W.float().cpu().t()
+    if sw:
+        r = ref.view(B, N // 16, 2, 8)
+        ref = (torch.nn.functional.silu(r[:, :, 0]) * r[:, :, 1]).reshape(B, N // 2)
+    if R is not None:
+        ref = ref + R.float().cpu()
+    assert_close_kernel(Y, ref, f"skinny {B}x{N}x{K}")
+
+
+def test_norms():
+    lib = _lib.load()
+    torch.manual_seed(1)
+    x = (torch.randn(1155, 1024, device=DEV) * 2 + 0.3).half()
+    w = (1 + 0.1 * torch.randn(1024, device=DEV)).half()
+    b = (0.1 * torch.randn(1024, device=DEV)).half()
+    y = torch.empty_like(x)
+    _lib.check(lib.vcb_op_layernorm_f16(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(y), x.shape[0], 1024, 1e-5, ST))
+    ref = torch.nn.functional.layer_norm(x.float().cpu(), (1024,), w.float().cpu(), b.float().cpu(), 1e-5)
+    assert_close_kernel(y, ref, "layernorm")
+    x = (torch.randn(77, 4096, device=DEV) * 3).half()
+    w = (1 + 0.1 * torch.randn(4096, device=DEV)).half()
+    y = torch.empty_like(x)
+    _lib.check(lib.vcb_op_rmsnorm_f16(_lib.ptr(x), _lib.ptr(w), _lib.ptr(y), 77, 4096, 1e-5, ST))
+    assert_close_kernel(y, orc.rms_norm(x.float().cpu(), w.float().cpu(), 1e-5), "rmsnorm")
+
+
+@pytest.mark.parametrize("B,S,heads,scale_q", [(2, 577, 16, 1.0), (1, 17, 2, 2.0), (3, 130, 4, 3.0), (1, 64, 1, 1.0), (1, 65, 1, 1.0)])
+def test_attention_vit(B, S, heads, scale_q):
+    lib = _lib.load()
+    torch.manual_seed(S)
+    D = heads * 64
+    qkv = torch.randn(B * S, 3 * D, device=DEV)
+    qkv[:, :D] *= scale_q  # sharper softmax than random init gives
+    qkv = qkv.half()
+    o = torch.full((B * S, D), float("nan"), device=DEV, dtype=torch.float16)
+    _lib.check(lib.vcb_op_attention_vit_f16(_lib.ptr(qkv), B, S, heads, 0.125, _lib.ptr(o), ST))
+    torch.cuda.synchronize()
+    q, k, v = [t.float().cpu().view(B, S, heads, 64).transpose(1, 2) for t in qkv.split(D, dim=1)]
+    ref = (torch.softmax(q @ k.transpose(-1, -2) * 0.125, -1) @ v).transpose(1, 2).reshape(B * S, D)
+    assert rel_rms(o, ref) <= 1.5e-3 and max_abs(o, ref) <= 4e-3, (rel_rms(o, ref), max_abs(o, ref))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# engine level, tiny geometry: against the oracle AND the fixtures written by the reference itself
+# ---------------------------------------------------------------------------------------------------------------
+def _tiny(variant):
+    g = synth.PRESETS["tiny"].with_variant(variant)
+    sd = synth.make_state_dict(g, seed=0)
+    fname = "tiny_ds.npz" if variant == synth.VARIANT_VCODER_DS else "tiny_vcoder.npz"
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", fname))
+    assert synth.state_dict_digest(sd) == str(z["weights_digest"])
+    B = z["ids"].shape[0]
+    images, segs = synth.make_pixels(g, B, 1), synth.make_pixels(g, B, 2)
+    depths = synth.make_pixels(g, B, 3) if variant == synth.VARIANT_VCODER_DS else None
+    eng = Engine(g, max_batch=B, max_seq_len=128)
+    eng.bind(sd)
+    return g, sd, z, eng, torch.from_numpy(z["ids"]), images, segs, depths
+
+
+def check_greedy(got_ids, got_logits, ref_ids, ref_logits, logit_tol):
+    """Teacher-forced comparison: stop following a row after its first (margin-justified) divergence."""
+    B, N = ref_ids.shape
+    alive = torch.ones(B, dtype=torch.bool)
+    for s in range(N):
+        lg, rl = got_logits[s].float().cpu(), ref_logits[s].float().cpu()
+        err = (lg - rl).abs().max(dim=-1).values
+        assert bool((err[alive] <= logit_tol).all()), f"step {s}: logit error {err.tolist()} > {logit_tol}"
+        top2 = rl.topk(2, dim=-1).values
+        margin = top2[:, 0] - top2[:, 1]
+        same = got_ids[:, s].cpu().long() == ref_ids[:, s]
+        bad = alive & ~same & (margin > 2 * logit_tol)
+        assert not bool(bad.any()), f"step {s}: ids {got_ids[:, s].tolist()} vs {ref_ids[:, s].tolist()}, margins {margin.tolist()}"
+        alive &= same
+    return alive
+
+
+@pytest.mark.parametrize("variant", [synth.VARIANT_VCODER_DS, synth.VARIANT_VCODER])
+def test_tiny_against_reference_golden(variant):
+    g, sd, z, eng, ids, images, segs, depths = _tiny(variant)
+    tower = eng.tower_forward(images)
+    assert rel_rms(tower, torch.from_numpy(z["tower_features"])) <= 4e-3
+    assert rel_rms(eng.encode(0, images), torch.from_numpy(z["image_features"])) <= 4e-3
+    assert rel_rms(eng.encode(1, segs), torch.from_numpy(z["seg_features"])) <= 4e-3
+    if depths is not None:
+        assert rel_rms(eng.encode(2, depths), torch.from_numpy(z["depth_features"])) <= 4e-3  # via seg_mm_projector
+    pre = eng.prefill(ids, images, segs, depths, want_logits=True, want_embeds=True)
+    assert pre["spliced_len"] == z["inputs_embeds"].shape[1]
+    assert rel_rms(pre["embeds"], torch.from_numpy(z["inputs_embeds"])) <= 4e-3
+    n_new = z["greedy_ids"].shape[1]
+    dec_ids, dec_logits = eng.decode(n_new - 1, want_logits=True)
+    torch.cuda.synchronize()
+    got_ids = torch.cat([pre["next_ids"][:, None], dec_ids], dim=1)
+    got_logits = [pre["logits"]] + [dec_logits[s] for s in range(n_new - 1)]
+    ref_logits = [torch.from_numpy(z["step_logits"][s]) for s in range(n_new)]
+    alive = check_greedy(got_ids, got_logits, torch.from_numpy(z["greedy_ids"]), ref_logits, logit_tol=3e-2)
+    assert bool(alive.any())
+    # the CUDA-graph + host-buffer path (vcb_generate) must reproduce the eager path exactly
+    gen = eng.generate(ids, images, segs, depths, max_new_tokens=n_new)
+    assert torch.equal(gen, got_ids.cpu().long())
+    gen2 = eng.generate(ids, images, segs, depths, max_new_tokens=n_new)  # graph replay, fresh KV cache
+    assert torch.equal(gen2, gen)
+
+
+def test_tiny_quirks_on_device():
+    g, sd, z, eng, ids, images, segs, depths = _tiny(synth.VARIANT_VCODER_DS)
+    I, S, D = synth.IMAGE_TOKEN_INDEX, synth.SEG_TOKEN_INDEX, synth.DEPTH_TOKEN_INDEX
+    # F5: with the tokenizer's [IMAGE, DEPTH, SEG] order the depth image cannot influence the output
+    a = eng.generate(ids, images, segs, depths, max_new_tokens=4)
+    b = eng.generate(ids, images, segs, synth.make_pixels(g, ids.shape[0], 9), max_new_tokens=4)
+    assert torch.equal(a, b)
+    # depth AFTER seg is spliced: T' grows by P, and matches the oracle
+    ids2 = torch.tensor([[1, 7, I, 9, S, 11, D, 13], [1, 8, I, 10, S, 12, D, 14]])
+    pre = eng.prefill(ids2, images, segs, depths, want_logits=True, want_embeds=True)
+    x_ref = orc.prefill_embeds(ids2, sd, g, images, segs, depths)
+    assert pre["spliced_len"] == x_ref.shape[1] == 8 - 3 - 1 + 3 * g.n_patches
+    assert rel_rms(pre["embeds"], x_ref) <= 4e-3
+    # all-zero depth image + reachable <depth> token -> the reference's IndexError
+    with pytest.raises(_lib.VcbError) as ei:
+        eng.prefill(ids2, images, segs, torch.zeros_like(depths))
+    assert ei.value.code == -6
+    # ragged batch -> the reference's NameError
+    with pytest.raises(_lib.VcbError) as ei:
+        eng.prefill(torch.tensor([[1, I, S, 5], [1, 5, 6, 7]]), images, segs, depths)
+    assert ei.value.code == -5
+    # text-only prompt (images=None) runs the plain LLaMA path
+    t_ids = torch.randint(3, g.llm_vocab, (2, 9))
+    pre = eng.prefill(t_ids, None, None, None, want_logits=True)
+    emb = sd["model.embed_tokens.weight"].float()[t_ids]
+    ref = orc.llama_forward(emb, sd, g, orc.KVCache(g.llm_layers))
+    assert max_abs(pre["logits"], ref) <= 3e-2
+
+
+def test_decode_equals_prefill_property():
+    """Size-independent property: logits after prefill(T) + decode(1 step on token x) == prefill(T+1 with x appended)."""
+    g, sd, z, eng, ids, images, segs, depths = _tiny(synth.VARIANT_VCODER_DS)
+    pre = eng.prefill(ids, images, segs, depths, want_logits=True)
+    nxt = pre["next_ids"].cpu().long()
+    _, lg = eng.decode(1, want_logits=True)
+    ids_ext = torch.cat([ids, nxt[:, None]], dim=1)
+    pre2 = eng.prefill(ids_ext, images, segs, depths, want_logits=True)
+    assert max_abs(lg[0], pre2["logits"]) <= 2e-2

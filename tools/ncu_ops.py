@@ -1,0 +1,48 @@
+"""Launch the hot kernels at their production shapes a few times each (for `ncu -k regex:...`)."""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from vcoder_b200 import _lib  # noqa: E402
+
+lib = _lib.load()
+dev = "cuda"
+st = C.c_void_p(0)
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+torch.manual_seed(0)
+flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+if which in ("all", "skinny"):
+    B = 8
+    for (N, K, sw) in [(12288, 4096, 0), (4096, 4096, 0), (22016, 4096, 1), (4096, 11008, 0), (32000, 4096, 0)]:
+        X = (torch.randn(B, K, device=dev) * 0.5).half()
+        W = (torch.randn(N, K, device=dev) * 0.03).half()
+        No = N // 2 if sw else N
+        Y = torch.empty(B, No, device=dev, dtype=torch.float16)
+        for _ in range(3):
+            flush.zero_()
+            lib.vcb_op_skinny_gemm_f16(_lib.ptr(X), K, _lib.ptr(W), B, N, K, None, N, sw, _lib.ptr(Y), No, st)
+        torch.cuda.synchronize()
+if which in ("all", "attn"):
+    Bi, S, heads = 24, 577, 16
+    D = heads * 64
+    qkv = torch.randn(Bi * S, 3 * D, device=dev).half()
+    o = torch.empty(Bi * S, D, device=dev, dtype=torch.float16)
+    for _ in range(3):
+        flush.zero_()
+        lib.vcb_op_attention_vit_f16(_lib.ptr(qkv), Bi, S, heads, 0.125, _lib.ptr(o), st)
+    torch.cuda.synchronize()
+if which in ("all", "gemm"):
+    for (M, N, K, act) in [(13848, 3072, 1024, 0), (13848, 4096, 1024, 1), (13848, 1024, 4096, 0), (9656, 12288, 4096, 0), (9656, 22016, 4096, 3), (9656, 4096, 11008, 0)]:
+        A = (torch.randn(M, K, device=dev) * 0.5).half()
+        W = (torch.randn(N, K, device=dev) * 0.03).half()
+        No = N // 2 if act == 3 else N
+        Cc = torch.empty(M, No, device=dev, dtype=torch.float16)
+        for _ in range(2):
+            lib.vcb_op_gemm_f16(_lib.ptr(A), K, _lib.ptr(W), K, M, N, K, None, None, N, act, _lib.ptr(Cc), No, 0, st)
+        torch.cuda.synchronize()
+print("done")

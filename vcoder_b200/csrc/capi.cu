@@ -51,3 +51,181 @@ int vcb_op_gemm_f16(const vcb_half* A, int32_t lda, const vcb_half* W, int32_t l
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------
+#include <vector>
+
+#include "engine.h"
+#include "kernels.h"
+
+struct vcb_engine {
+  vcb::Engine* e;
+};
+
+namespace {
+inline const __half* H(const vcb_half* p) { return reinterpret_cast<const __half*>(p); }
+inline __half* H(vcb_half* p) { return reinterpret_cast<__half*>(p); }
+inline cudaStream_t ST(void* s) { return static_cast<cudaStream_t>(s); }
+}  // namespace
+
+extern "C" {
+
+int vcb_op_skinny_gemm_f16(const vcb_half* X, int32_t ldx, const vcb_half* W, int32_t B, int32_t N, int32_t K,
+                           const vcb_half* residual, int32_t ldr, int32_t swiglu, vcb_half* Y, int32_t ldy,
+                           void* stream) {
+  VCB_TRY(require_device());
+  SkinnyParams s;
+  s.X = H(X); s.ldx = ldx; s.W = H(W); s.Y = H(Y); s.ldy = ldy; s.residual = H(residual); s.ldr = ldr;
+  s.B = B; s.N = N; s.K = K; s.swiglu = swiglu;
+  return skinny_gemm(s, ST(stream));
+}
+
+int vcb_op_layernorm_f16(const vcb_half* x, const vcb_half* w, const vcb_half* b, vcb_half* y, int64_t rows, int32_t D,
+                         float eps, void* stream) {
+  VCB_TRY(require_device());
+  return layernorm_f16(H(x), H(w), H(b), H(y), rows, D, eps, ST(stream));
+}
+
+int vcb_op_rmsnorm_f16(const vcb_half* x, const vcb_half* w, vcb_half* y, int64_t rows, int32_t Hd, float eps,
+                       void* stream) {
+  VCB_TRY(require_device());
+  return rmsnorm_f16(H(x), H(w), H(y), rows, Hd, eps, ST(stream));
+}
+
+int vcb_op_attention_vit_f16(const vcb_half* qkv, int32_t B, int32_t S, int32_t heads, float scale, vcb_half* out,
+                             void* stream) {
+  VCB_TRY(require_device());
+  const int D = heads * 64;
+  AttnPrefillParams a;
+  a.q = H(qkv); a.k = a.q + D; a.v = a.q + 2 * D;
+  a.q_stride = 3 * D; a.kv_stride = 3 * D;
+  a.out = H(out); a.out_stride = D;
+  a.batch = B; a.n_heads = heads; a.seq_len = S; a.head_dim = 64; a.scale = scale;
+  return attn_vit(a, ST(stream));
+}
+
+int vcb_splice_plan(int32_t variant, const int64_t* ids, int32_t B, int32_t T, int32_t n_patches, int32_t has_seg,
+                    const uint8_t* depth_nonzero, int32_t* plan_out, int64_t plan_cap, int32_t* out_len) {
+  VCB_CHECK(ids != nullptr && out_len != nullptr && B >= 1 && T >= 1, kErrInvalid, "vcb_splice_plan: bad arguments");
+  VCB_CHECK(variant == VCB_VARIANT_VCODER || variant == VCB_VARIANT_VCODER_DS, kErrInvalid, "bad variant");
+  std::vector<int32_t> plan;
+  int len = 0;
+  VCB_TRY(splice_plan_host(variant, ids, B, T, n_patches, has_seg, depth_nonzero, &plan, &len, nullptr));
+  *out_len = len;
+  if (plan_out) {
+    VCB_CHECK(static_cast<int64_t>(plan.size()) <= plan_cap, kErrNoMem, "vcb_splice_plan: plan_out too small");
+    std::copy(plan.begin(), plan.end(), plan_out);
+  }
+  return kOk;
+}
+
+int vcb_create(const vcb_config* cfg, int32_t device, vcb_handle* out) {
+  VCB_TRY(require_device());
+  VCB_CHECK(out != nullptr, kErrInvalid, "vcb_create: null out");
+  Engine* e = nullptr;
+  VCB_TRY(engine_create(cfg, device, &e));
+  *out = new vcb_engine{e};
+  return kOk;
+}
+
+int vcb_destroy(vcb_handle h) {
+  if (h) {
+    delete h->e;
+    delete h;
+  }
+  return kOk;
+}
+
+int vcb_bind_weights(vcb_handle h, const vcb_tensor* tensors, int32_t n) {
+  VCB_CHECK(h != nullptr, kErrInvalid, "null handle");
+  return engine_bind(h->e, tensors, n);
+}
+
+int vcb_tower_forward(vcb_handle h, const vcb_half* pixels, int32_t n, vcb_half* out, void* stream) {
+  VCB_CHECK(h != nullptr && pixels != nullptr && out != nullptr, kErrInvalid, "vcb_tower_forward: null argument");
+  Engine* e = h->e;
+  VCB_CUDA(cudaSetDevice(e->device));
+  VCB_TRY(engine_check_bound(e, true, false));
+  VCB_CHECK(n >= 1 && n <= e->vit_max_images, kErrInvalid, "vcb_tower_forward: n must be in [1, 3*max_batch]");
+  const size_t img = 3ul * e->cfg.vit_image_size * e->cfg.vit_image_size * 2;
+  StreamGuard sg(e, ST(stream));
+  VCB_TRY(copy_any(e->pix.p, pixels, n * img, sg.st));
+  VCB_TRY(engine_tower(e, e->pix.as<__half>(), n, sg.st));
+  // feature_select 'patch': drop CLS; compact into vn then copy out (out may be host memory)
+  VCB_TRY(compact_patches(e->vh.as<__half>(), e->vn.as<__half>(), n, e->S, e->cfg.vit_hidden, sg.st));
+  return copy_any(out, e->vn.p, static_cast<size_t>(n) * e->P * e->cfg.vit_hidden * 2, sg.st);
+}
+
+int vcb_encode(vcb_handle h, int32_t modality, const vcb_half* pixels, int32_t n, vcb_half* out, void* stream) {
+  VCB_CHECK(h != nullptr && pixels != nullptr && out != nullptr, kErrInvalid, "vcb_encode: null argument");
+  VCB_CHECK(modality >= 0 && modality <= 2, kErrInvalid, "vcb_encode: modality must be 0 (rgb), 1 (seg) or 2 (depth)");
+  Engine* e = h->e;
+  VCB_CUDA(cudaSetDevice(e->device));
+  VCB_TRY(engine_check_bound(e, true, true));
+  VCB_CHECK(n >= 1 && n <= e->vit_max_images, kErrInvalid, "vcb_encode: n must be in [1, 3*max_batch]");
+  const size_t img = 3ul * e->cfg.vit_image_size * e->cfg.vit_image_size * 2;
+  StreamGuard sg(e, ST(stream));
+  VCB_TRY(copy_any(e->pix.p, pixels, n * img, sg.st));
+  VCB_TRY(engine_tower(e, e->pix.as<__half>(), n, sg.st));
+  VCB_TRY(engine_project(e, 0, n * e->S, modality == 0 ? e->mm : e->seg, sg.st));
+  VCB_TRY(compact_patches(e->feats.as<__half>(), e->pmid.as<__half>(), n, e->S, e->cfg.llm_hidden, sg.st));
+  return copy_any(out, e->pmid.p, static_cast<size_t>(n) * e->P * e->cfg.llm_hidden * 2, sg.st);
+}
+
+int vcb_prefill(vcb_handle h, const int64_t* ids, int32_t B, int32_t T, const vcb_half* images, const vcb_half* segs,
+                const vcb_half* depths, int32_t* next_ids, vcb_half* last_logits, vcb_half* embeds, int32_t* spliced_len,
+                void* stream) {
+  VCB_CHECK(h != nullptr, kErrInvalid, "null handle");
+  int len = 0;
+  StreamGuard sg(h->e, ST(stream));
+  VCB_TRY(engine_prefill(h->e, ids, B, T, images, segs, depths, next_ids, last_logits, embeds, &len, sg.st));
+  if (spliced_len) *spliced_len = len;
+  return kOk;
+}
+
+int vcb_decode(vcb_handle h, int32_t n_steps, int32_t* out_ids, vcb_half* logits_trace, void* stream) {
+  VCB_CHECK(h != nullptr, kErrInvalid, "null handle");
+  StreamGuard sg(h->e, ST(stream));
+  return engine_decode(h->e, n_steps, out_ids, logits_trace, sg.st);
+}
+
+int vcb_generate(vcb_handle h, const int64_t* ids, int32_t B, int32_t T, const vcb_half* images, const vcb_half* segs,
+                 const vcb_half* depths, int32_t max_new_tokens, int64_t* out_ids, void* stream) {
+  VCB_CHECK(h != nullptr && out_ids != nullptr, kErrInvalid, "vcb_generate: null argument");
+  VCB_CHECK(max_new_tokens >= 1, kErrInvalid, "vcb_generate: max_new_tokens must be >= 1");
+  Engine* e = h->e;
+  StreamGuard sg(e, ST(stream));
+  VCB_TRY(engine_prefill(e, ids, B, T, images, segs, depths, nullptr, nullptr, nullptr, nullptr, sg.st));
+  VCB_TRY(engine_decode(e, max_new_tokens - 1, nullptr, nullptr, sg.st));
+  std::vector<int32_t> tmp(static_cast<size_t>(B) * max_new_tokens);
+  VCB_CUDA(cudaMemcpy2DAsync(tmp.data(), static_cast<size_t>(max_new_tokens) * 4, e->trace.p,
+                             static_cast<size_t>(e->cfg.max_seq_len) * 4, static_cast<size_t>(max_new_tokens) * 4, B,
+                             cudaMemcpyDeviceToHost, sg.st));
+  VCB_CUDA(cudaStreamSynchronize(sg.st));
+  for (size_t i = 0; i < tmp.size(); ++i) out_ids[i] = tmp[i];
+  return kOk;
+}
+
+int vcb_reset(vcb_handle h) {
+  VCB_CHECK(h != nullptr, kErrInvalid, "null handle");
+  return engine_reset(h->e);
+}
+
+}  // extern "C"
+
+extern "C" {
+
+uint64_t vcb_launch_count(void) { return vcb::launch_count(); }
+
+int vcb_profile_enable(int32_t on) {
+  vcb::prof_enable(on != 0);
+  return vcb::kOk;
+}
+
+int vcb_profile_read(float* ms_by_category, uint64_t* launches_by_category, int32_t n_categories) {
+  VCB_CHECK(ms_by_category != nullptr && launches_by_category != nullptr && n_categories == vcb::kNumCat, vcb::kErrInvalid,
+            "vcb_profile_read: need arrays of VCB_PROFILE_CATEGORIES entries");
+  return vcb::prof_read(ms_by_category, launches_by_category);
+}
+
+}  // extern "C"

@@ -75,4 +75,21 @@ int gemm_f16(const __half* A, int lda, const __half* W, int ldw, int M, int N, i
 
 int device_sm_count();
 
+// -------------------------------------------------------------------------------------------------
+// launch accounting / profiling (profile.cu)
+// -------------------------------------------------------------------------------------------------
+enum KernelCat : int {
+  kCatGemm = 0, kCatSkinny, kCatAttnVit, kCatAttnPrefill, kCatAttnDecode, kCatNorm, kCatRope, kCatMisc, kNumCat
+};
+struct KernelScope {  // RAII around one launcher call: counts kernels, optionally brackets them with events
+  KernelScope(int cat, cudaStream_t st, int n_kernels = 1);
+  ~KernelScope();
+  int cat_; cudaStream_t st_; int rec_;
+};
+uint64_t launch_count();
+void launch_count_add(int64_t n);
+void prof_enable(bool on);
+bool prof_enabled();
+int prof_read(float* ms_by_cat, uint64_t* n_by_cat);
+
 }  // namespace vcb

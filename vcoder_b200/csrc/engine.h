@@ -1,0 +1,109 @@
+// Engine: owns packed weights, workspaces, the paged KV cache and the decode CUDA graph for one model on one GPU.
+#pragma once
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "common.h"
+#include "kernels.h"
+#include "vcoder_b200.h"
+
+namespace vcb {
+
+// Host-side splice planner (pure C++, no CUDA): restates prepare_inputs_labels_for_multimodal
+// (vcoder_ds_llava_arch.py:175-312 / vcoder_llava_arch.py:182-294).  plan[b*T_out + t]:
+//   >= 0 token id (row of embed_tokens), -1 zero pad, <= -2 feature row -(v+2) of the [kinds*B*tokens] feature buffer.
+int splice_plan_host(int variant, const int64_t* ids, int B, int T, int n_patches, int has_seg,
+                     const uint8_t* depth_nonzero /* null = depths is None */, std::vector<int32_t>* plan,
+                     int* out_len, bool* depth_flag_needed);
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  template <typename T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct VitLayerW {
+  DevBuf qkv_w, qkv_b, out_w, out_b, ln1_w, ln1_b, ln2_w, ln2_b, fc1_w, fc1_b, fc2_w, fc2_b;
+};
+struct ProjW {
+  DevBuf w1, b1, w2, b2;
+};
+struct LlmLayerW {
+  DevBuf qkv_w, o_w, gu_w, down_w, ln1, ln2;
+};
+
+struct Engine {
+  vcb_config cfg{};
+  int device = 0;
+  // derived
+  int P = 0;        // patches per image
+  int S = 0;        // tokens per image (P + 1)
+  int Kpe = 0;      // padded im2col K
+  int vit_used = 0; // encoder layers actually evaluated
+  int max_pages_per_seq = 0, n_pages = 0;
+  int vit_max_images = 0;
+  long max_rows = 0;  // LLM prefill rows (max_batch * max_seq_len)
+
+  // weights
+  DevBuf patch_w, cls, pos, preln_w, preln_b;
+  std::vector<VitLayerW> vit;
+  ProjW mm, seg;
+  DevBuf embed, final_norm, lm_head;
+  std::vector<LlmLayerW> llm;
+  std::set<std::string> bound;
+
+  // workspaces
+  DevBuf pix, im2col, vh, vn, vqkv, vattn, vmid;  // vision
+  DevBuf pmid, feats;                             // projector
+  DevBuf x, xn, qkv, attn, mid;                   // LLM prefill
+  DevBuf xd, xnd, qkvd, attnd, midd;              // LLM decode (B rows)
+  DevBuf logits, next_ids, trace, part_o, part_ml, plan_dev, depth_sums;
+  DevBuf k_pool, v_pool, block_table, rope, counters;  // counters: [0] cache_len, [1] step
+  int32_t* plan_host = nullptr;                        // pinned
+  int32_t* bt_host = nullptr;                          // pinned
+  float* depth_host = nullptr;                         // pinned
+  std::vector<void*> allocs;
+
+  // state
+  int batch = 0;
+  int cache_len = 0;  // host mirror
+  int steps_done = 0; // tokens produced since the last prefill
+  int pages_per_seq_alloc = 0;
+  bool prefilled = false;
+  cudaGraphExec_t graph = nullptr;
+  cudaStream_t own_stream = nullptr;   // used when the caller hands us the legacy default stream
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  int graph_batch = 0, graph_splits = 0, graph_kernels = 0;
+
+  ~Engine();
+};
+
+int engine_create(const vcb_config* cfg, int device, Engine** out);
+int engine_bind(Engine* e, const vcb_tensor* t, int n);
+int engine_check_bound(Engine* e, bool need_vision, bool need_llm);
+// images: device pointer to n images [n,3,S,S] fp16 already resident; result rows in e->vh ([n*S, D])
+int engine_tower(Engine* e, const __half* pixels_dev, int n_images, cudaStream_t st);
+int engine_project(Engine* e, int row_begin, int row_end, const ProjW& w, cudaStream_t st);
+int engine_prefill(Engine* e, const int64_t* ids_host, int B, int T, const void* images, const void* segs,
+                   const void* depths, void* next_ids_out, void* last_logits_out, void* embeds_out, int* spliced_len,
+                   cudaStream_t st);
+int engine_decode(Engine* e, int n_steps, void* out_ids, void* logits_trace, cudaStream_t st);
+int engine_reset(Engine* e);
+int copy_any(void* dst, const void* src, size_t bytes, cudaStream_t st);
+
+// Work always runs on a capturable (non-legacy) stream.  When the caller passes NULL / the legacy default stream,
+// the engine's own stream is ordered after the caller's prior work on entry and the caller's stream waits for the
+// engine's work on exit, so the usual stream semantics are preserved.
+struct StreamGuard {
+  StreamGuard(Engine* e, cudaStream_t caller);
+  ~StreamGuard();
+  cudaStream_t st;
+  Engine* e_;
+  cudaStream_t caller_;
+  bool swapped_;
+};
+
+}  // namespace vcb

@@ -266,6 +266,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpilogue& e
   const int tiles_m = (M + BM - 1) / BM;
   const int tiles_n = (N + BN - 1) / BN;
   const int grid = std::min(tiles_m * tiles_n, device_sm_count());
+  KernelScope scope(kCatGemm, stream);
   gemm_tc5_kernel<BN, ACT><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, ep, M, N, K, tiles_m, tiles_n);
   VCB_CUDA(cudaGetLastError());
   return kOk;

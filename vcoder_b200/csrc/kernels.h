@@ -1,0 +1,83 @@
+// Internal launcher declarations for the non-GEMM kernels of libvcoder_b200.
+#pragma once
+#include "common.h"
+
+namespace vcb {
+
+// ---- attention -----------------------------------------------------------------------------------
+struct AttnPrefillParams {
+  // dense path (ViT): q/k/v are column blocks of one [B*S, 3*D] buffer
+  const __half* q = nullptr;
+  const __half* k = nullptr;
+  const __half* v = nullptr;
+  long q_stride = 0;   // elements between consecutive tokens of q
+  long kv_stride = 0;  // same for k/v (dense path)
+  // paged path (LLaMA): K/V pools laid out [page][head][page_tokens][head_dim]
+  const __half* k_pool = nullptr;
+  const __half* v_pool = nullptr;
+  const int32_t* block_table = nullptr;  // [batch][max_pages]
+  int max_pages = 0;
+  int page_tokens = 0;
+  __half* out = nullptr;  // [B*S, heads*head_dim]
+  long out_stride = 0;
+  int batch = 0, n_heads = 0, seq_len = 0, head_dim = 0;
+  float scale = 1.f;
+};
+int attn_vit(const AttnPrefillParams& p, cudaStream_t stream);
+int attn_llama_prefill(const AttnPrefillParams& p, cudaStream_t stream);
+
+struct AttnDecodeParams {
+  const __half* q = nullptr;  // [B, 3H] (rotated q in the first H columns), stride q_stride
+  long q_stride = 0;
+  const __half* k_pool = nullptr;
+  const __half* v_pool = nullptr;
+  const int32_t* block_table = nullptr;
+  int max_pages = 0, page_tokens = 0;
+  const int32_t* ctx_len = nullptr;  // device scalar: number of cached tokens INCLUDING the current one
+  int max_ctx = 0;                   // host upper bound used to size the grid
+  float* part_o = nullptr;           // [B*heads, splits, 128]
+  float* part_ml = nullptr;          // [B*heads, splits, 2]
+  __half* out = nullptr;             // [B, H]
+  int batch = 0, n_heads = 0;
+  float scale = 1.f;
+};
+int attn_llama_decode(const AttnDecodeParams& p, cudaStream_t stream);
+int attn_decode_splits(int max_ctx);
+
+// ---- skinny GEMM (decode / lm_head): Y[B,N] = X[B,K] * W[N,K]^T ---------------------------------------
+struct SkinnyParams {
+  const __half* X = nullptr;  // [B, K], ldx
+  long ldx = 0;
+  const __half* W = nullptr;  // [N, K] row-major
+  __half* Y = nullptr;        // [B, N_out], ldy
+  long ldy = 0;
+  const __half* residual = nullptr;  // [B, N], ldr (may alias Y)
+  long ldr = 0;
+  int B = 0, N = 0, K = 0;
+  int swiglu = 0;  // W rows 8/8 interleaved gate|up; N_out = N/2
+};
+int skinny_gemm(const SkinnyParams& p, cudaStream_t stream);
+
+// ---- elementwise / normalisation / data movement ----------------------------------------------------------
+int im2col_patches(const __half* pixels, __half* out, int B, int image, int patch, int k_pad, cudaStream_t s);
+int write_cls_rows(const __half* cls, const __half* pos, __half* hidden, int B, int tokens, int D, cudaStream_t s);
+int layernorm_f16(const __half* x, const __half* w, const __half* b, __half* y, long rows, int D, float eps,
+                  cudaStream_t s);
+int rmsnorm_f16(const __half* x, const __half* w, __half* y, long rows, int H, float eps, cudaStream_t s);
+// rows of qkv [M,3H]: rotate q in place, write rotated k and v into the paged cache.
+// position of row m = pos0 (host) or *pos0_dev (device scalar, decode) + (m % T)
+int rope_kv_write(__half* qkv, int B, int T, int H, int n_heads, const float2* cos_sin, int pos0,
+                  const int32_t* pos0_dev, __half* k_pool, __half* v_pool, const int32_t* block_table, int max_pages,
+                  int page_tokens, cudaStream_t s);
+// out[r] = plan[r] >= 0 ? embed[plan[r]] : plan[r] == -1 ? 0 : feats[-plan[r]-2]
+int splice_gather(const int32_t* plan, const __half* embed, const __half* feats, __half* out, long rows, int H,
+                  cudaStream_t s);
+int embed_gather(const int32_t* ids, const __half* embed, __half* out, int B, int H, cudaStream_t s);
+// first-index argmax over fp16 logits [B,V]; writes next[b] and (optionally) trace[b*trace_stride + *step]
+int argmax_rows(const __half* logits, int B, int V, int32_t* next, int32_t* trace, int trace_stride,
+                const int32_t* step_dev, cudaStream_t s);
+int compact_patches(const __half* hidden, __half* out, int B, int tokens, int D, cudaStream_t s);
+int advance_counters(int32_t* counters, cudaStream_t s);
+void build_rope_table(float2* host_table, int max_pos, int head_dim, float theta);
+
+}  // namespace vcb

@@ -1,0 +1,68 @@
+// Launch accounting and optional per-kernel-category timing (CUDA events on the launching stream).
+// bench.py uses it for `gpu_launches` and for the live roofline numbers of the dominant kernel.
+#include <atomic>
+#include <mutex>
+#include <vector>
+
+#include "common.h"
+
+namespace vcb {
+namespace {
+std::atomic<uint64_t> g_launches{0};
+std::atomic<uint64_t> g_cat_launches[kNumCat];
+bool g_prof = false;
+struct Rec { int cat; cudaEvent_t a, b; };
+std::vector<Rec> g_recs;
+std::vector<cudaEvent_t> g_pool;
+std::mutex g_mu;
+
+cudaEvent_t get_event() {
+  if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+}  // namespace
+
+uint64_t launch_count() { return g_launches.load(); }
+void launch_count_add(int64_t n) { g_launches.fetch_add(static_cast<uint64_t>(n)); }
+bool prof_enabled() { return g_prof; }
+
+void prof_enable(bool on) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (auto& r : g_recs) { g_pool.push_back(r.a); g_pool.push_back(r.b); }
+  g_recs.clear();
+  g_prof = on;
+}
+
+KernelScope::KernelScope(int cat, cudaStream_t st, int n_kernels) : cat_(cat), st_(st), rec_(-1) {
+  g_launches.fetch_add(n_kernels);
+  g_cat_launches[cat].fetch_add(n_kernels);
+  if (g_prof) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    Rec r{cat, get_event(), get_event()};
+    cudaEventRecord(r.a, st);
+    g_recs.push_back(r);
+    rec_ = static_cast<int>(g_recs.size()) - 1;
+  }
+}
+KernelScope::~KernelScope() {
+  if (rec_ >= 0) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (rec_ < static_cast<int>(g_recs.size())) cudaEventRecord(g_recs[rec_].b, st_);
+  }
+}
+
+// ms_by_cat / n_by_cat: arrays of kNumCat. Synchronises the device.
+int prof_read(float* ms_by_cat, uint64_t* n_by_cat) {
+  VCB_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (int c = 0; c < kNumCat; ++c) { ms_by_cat[c] = 0.f; n_by_cat[c] = 0; }
+  for (auto& r : g_recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { ms_by_cat[r.cat] += ms; n_by_cat[r.cat] += 1; }
+  }
+  return kOk;
+}
+
+}  // namespace vcb

@@ -1,0 +1,167 @@
+"""Python handle over the C-ABI engine (vcb_create / vcb_bind_weights / vcb_prefill / vcb_decode / vcb_generate).
+
+torch is used for device memory and streams only; every FLOP on the path runs inside libvcoder_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .synth import ModelGeometry
+
+
+def _stream_ptr() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _as_half_any(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """fp16, contiguous, on whatever device it already lives (host buffers are copied by the library)."""
+    if t is None:
+        return None
+    if t.dtype != torch.float16:
+        t = t.to(torch.float16)
+    return t.contiguous()
+
+
+class Engine:
+    def __init__(self, g: ModelGeometry, max_batch: int = 8, max_seq_len: int = 1536, device: int = 0):
+        if not torch.cuda.is_available():
+            # fail loudly: there is no CPU fallback anywhere in this package
+            raise RuntimeError("vcoder_b200.Engine needs a CUDA device (no CPU fallback exists)")
+        self.lib = _lib.load()
+        self.g = g
+        self.device = device
+        self.max_batch = max_batch
+        self.max_seq_len = max_seq_len
+        self.lock = threading.Lock()  # a handle is single-stream and not re-entrant
+        cfg = _lib.VcbConfig(
+            struct_size=C.sizeof(_lib.VcbConfig), variant=g.variant,
+            vit_image_size=g.vit_image_size, vit_patch=g.vit_patch, vit_hidden=g.vit_hidden, vit_heads=g.vit_heads,
+            vit_ffn=g.vit_ffn, vit_layers=g.vit_layers, vit_select_layer=g.vit_select_layer, vit_ln_eps=g.vit_ln_eps,
+            llm_hidden=g.llm_hidden, llm_layers=g.llm_layers, llm_heads=g.llm_heads, llm_ffn=g.llm_ffn,
+            llm_vocab=g.llm_vocab, llm_rms_eps=g.llm_rms_eps, llm_rope_theta=g.llm_rope_theta,
+            max_batch=max_batch, max_seq_len=max_seq_len, kv_page_tokens=64)
+        h = C.c_void_p()
+        _lib.check(self.lib.vcb_create(C.byref(cfg), device, C.byref(h)))
+        self.h = h
+        self.tdev = torch.device("cuda", device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vcb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------------
+    def bind(self, state_dict: Dict[str, torch.Tensor], chunk: int = 64) -> None:
+        """Copies (and packs) the named tensors into the handle; the caller may drop its copies afterwards."""
+        items = [(k, v) for k, v in state_dict.items() if torch.is_tensor(v) and v.dtype.is_floating_point]
+        for i in range(0, len(items), chunk):
+            part = items[i:i + chunk]
+            keep = []
+            arr = (_lib.VcbTensor * len(part))()
+            for j, (k, v) in enumerate(part):
+                t = v.detach()
+                if t.dtype != torch.float16:
+                    t = t.to(torch.float16)
+                t = t.contiguous()
+                keep.append(t)
+                arr[j].name = k.encode()
+                arr[j].data = t.data_ptr()
+                arr[j].ndim = t.dim()
+                for d in range(t.dim()):
+                    arr[j].shape[d] = t.shape[d]
+            _lib.check(self.lib.vcb_bind_weights(self.h, arr, len(part)))
+            del keep
+
+    # ------------------------------------------------------------------------------------------------
+    def tower_forward(self, pixels: torch.Tensor) -> torch.Tensor:
+        px = _as_half_any(pixels)
+        n = px.shape[0]
+        out = torch.empty(n, self.g.n_patches, self.g.vit_hidden, dtype=torch.float16, device=self.tdev)
+        with self.lock:
+            _lib.check(self.lib.vcb_tower_forward(self.h, _lib.ptr(px), n, _lib.ptr(out), _stream_ptr()))
+        return out
+
+    def encode(self, modality: int, pixels: torch.Tensor) -> torch.Tensor:
+        px = _as_half_any(pixels)
+        n = px.shape[0]
+        out = torch.empty(n, self.g.n_patches, self.g.llm_hidden, dtype=torch.float16, device=self.tdev)
+        with self.lock:
+            _lib.check(self.lib.vcb_encode(self.h, modality, _lib.ptr(px), n, _lib.ptr(out), _stream_ptr()))
+        return out
+
+    def prefill(self, ids: torch.Tensor, images=None, segs=None, depths=None, want_logits=False, want_embeds=False):
+        ids_h = ids.detach().to("cpu", torch.int64).contiguous()
+        B, T = ids_h.shape
+        self._last_batch = B
+        im, sg, dp = _as_half_any(images), _as_half_any(segs), _as_half_any(depths)
+        nxt = torch.empty(B, dtype=torch.int32, device=self.tdev)
+        logits = torch.empty(B, self.g.llm_vocab, dtype=torch.float16, device=self.tdev) if want_logits else None
+        n_vis = 3 * self.g.n_patches
+        embeds = (torch.empty(B, T + n_vis, self.g.llm_hidden, dtype=torch.float16, device=self.tdev)
+                  if want_embeds else None)
+        slen = C.c_int32(0)
+        with self.lock:
+            _lib.check(self.lib.vcb_prefill(self.h, _lib.ptr(ids_h), B, T, _lib.ptr(im), _lib.ptr(sg), _lib.ptr(dp),
+                                            _lib.ptr(nxt), _lib.ptr(logits), _lib.ptr(embeds), C.byref(slen),
+                                            _stream_ptr()))
+        out = {"next_ids": nxt, "spliced_len": slen.value}
+        if want_logits:
+            out["logits"] = logits
+        if want_embeds:
+            out["embeds"] = embeds.view(-1)[: B * slen.value * self.g.llm_hidden].view(B, slen.value, self.g.llm_hidden)
+        return out
+
+    def decode(self, n_steps: int, want_logits=False):
+        B = self._batch()
+        ids = torch.empty(B, n_steps, dtype=torch.int32, device=self.tdev)
+        trace = (torch.empty(n_steps, B, self.g.llm_vocab, dtype=torch.float16, device=self.tdev)
+                 if want_logits else None)
+        with self.lock:
+            _lib.check(self.lib.vcb_decode(self.h, n_steps, _lib.ptr(ids), _lib.ptr(trace), _stream_ptr()))
+        return (ids, trace) if want_logits else ids
+
+    def generate(self, ids: torch.Tensor, images=None, segs=None, depths=None, max_new_tokens: int = 32) -> torch.Tensor:
+        """HOST in, HOST out: the e2e entry (H2D of pixels/ids and D2H of the ids happen inside the call)."""
+        ids_h = ids.detach().to("cpu", torch.int64).contiguous()
+        B, T = ids_h.shape
+        self._last_batch = B
+        im, sg, dp = _as_half_any(images), _as_half_any(segs), _as_half_any(depths)
+        out = torch.empty(B, max_new_tokens, dtype=torch.int64)
+        with self.lock:
+            _lib.check(self.lib.vcb_generate(self.h, _lib.ptr(ids_h), B, T, _lib.ptr(im), _lib.ptr(sg), _lib.ptr(dp),
+                                             max_new_tokens, _lib.ptr(out), _stream_ptr()))
+        return out
+
+    def reset(self):
+        _lib.check(self.lib.vcb_reset(self.h))
+
+    def _batch(self) -> int:
+        return getattr(self, "_last_batch", None) or 0
+
+
+def splice_plan(variant: int, ids, n_patches: int, has_seg: bool = True, depth_nonzero=None):
+    """Host-only: the C++ splice planner (no GPU needed). Returns (plan [B, T'] int32 ndarray)."""
+    lib = _lib.load()
+    ids_np = np.ascontiguousarray(np.asarray(ids, dtype=np.int64))
+    B, T = ids_np.shape
+    cap = B * (T + 3 * n_patches)
+    plan = np.empty(cap, dtype=np.int32)
+    out_len = C.c_int32(0)
+    nz = None
+    if depth_nonzero is not None:
+        nz = np.ascontiguousarray(np.asarray(depth_nonzero, dtype=np.uint8))
+    _lib.check(lib.vcb_splice_plan(variant, _lib.ptr(ids_np), B, T, n_patches, int(has_seg), _lib.ptr(nz),
+                                   _lib.ptr(plan), cap, C.byref(out_len)))
+    return plan[: B * out_len.value].reshape(B, out_len.value)

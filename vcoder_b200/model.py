@@ -1,0 +1,212 @@
+"""Host-side mirror of the reference's model interface for the hot path — same names, argument meaning and error
+behaviour as the reference classes, with every computation dispatched to libvcoder_b200.so:
+
+    CLIPVisionTower                     vcoder_llava/model/multimodal_encoder/clip_encoder.py:7-77
+    VCoderLlavaLlamaForCausalLM         vcoder_llava/model/language_model/vcoder_llava_llama.py:41-139
+    VCoderDSLlavaLlamaForCausalLM       vcoder_llava/model/language_model/vcoder_ds_llava_llama.py:41-142
+    encode_images / encode_seg_images / encode_depth_images   vcoder_llava/model/vcoder_ds_llava_arch.py:106-119
+
+so that callers written against the reference (`model.generate(input_ids, images=, segs=, depths=, do_sample=False,
+max_new_tokens=..., use_cache=True, streamer=, stopping_criteria=)`, `model.get_vision_tower()`, `model.config`,
+`model.device`: serve/cli.py:121-132, eval/model_depth_loader.py:146-168, eval/model_seg_loader.py:127-149) keep working.
+"""
+from __future__ import annotations
+
+import types
+from typing import Dict, List, Optional
+
+import torch
+
+from . import synth
+from ._lib import VcbError
+from .engine import Engine
+from .synth import ModelGeometry
+
+
+class CLIPVisionTower:
+    """Mirror of clip_encoder.py:7 — one shared, frozen tower used for RGB, seg and depth."""
+
+    def __init__(self, engine: Engine, g: ModelGeometry, image_processor=None):
+        self._eng = engine
+        self._g = g
+        self.is_loaded = True
+        self.select_layer = g.vit_select_layer
+        self.select_feature = "patch"
+        self.image_processor = image_processor
+        self.config = types.SimpleNamespace(hidden_size=g.vit_hidden, image_size=g.vit_image_size,
+                                            patch_size=g.vit_patch, num_hidden_layers=g.vit_layers,
+                                            num_attention_heads=g.vit_heads, intermediate_size=g.vit_ffn)
+
+    def load_model(self):  # weights are bound into the engine at construction; kept for interface parity (:22-27)
+        self.is_loaded = True
+
+    @torch.no_grad()
+    def forward(self, images):
+        """clip_encoder.py:39-51: tensor [B,3,S,S] or a list of [3,S,S] -> hidden_states[select_layer][:, 1:]."""
+        if type(images) is list:
+            return [self._eng.tower_forward(im.unsqueeze(0)).to(im.dtype) for im in images]
+        return self._eng.tower_forward(images).to(images.dtype)
+
+    __call__ = forward
+
+    @property
+    def dtype(self):
+        return torch.float16
+
+    @property
+    def device(self):
+        return self._eng.tdev
+
+    @property
+    def hidden_size(self):
+        return self._g.vit_hidden
+
+    @property
+    def num_patches(self):
+        return self._g.n_patches
+
+    @property
+    def dummy_feature(self):
+        return torch.zeros(1, self.hidden_size, device=self.device, dtype=self.dtype)
+
+
+class _VCoderBase:
+    variant = synth.VARIANT_VCODER_DS
+    model_type = "vcoder_ds_llava"
+
+    def __init__(self, g: ModelGeometry, state_dict: Optional[Dict[str, torch.Tensor]] = None, max_batch: int = 8,
+                 max_seq_len: int = 2048, device: int = 0, image_processor=None):
+        g = g.with_variant(self.variant)
+        self.geometry = g
+        self._eng = Engine(g, max_batch=max_batch, max_seq_len=max_seq_len, device=device)
+        self._tower = CLIPVisionTower(self._eng, g, image_processor)
+        self.config = types.SimpleNamespace(
+            model_type=self.model_type, hidden_size=g.llm_hidden, intermediate_size=g.llm_ffn,
+            num_hidden_layers=g.llm_layers, num_attention_heads=g.llm_heads, vocab_size=g.llm_vocab,
+            rms_norm_eps=g.llm_rms_eps, max_position_embeddings=max_seq_len, mm_vision_select_layer=g.vit_select_layer,
+            mm_vision_select_feature="patch", mm_projector_type="mlp2x_gelu", seg_mm_projector_type="mlp2x_gelu",
+            mm_hidden_size=g.vit_hidden, use_cache=True, pad_token_id=0, bos_token_id=1, eos_token_id=2)
+        if state_dict is not None:
+            self.load_state_dict(state_dict)
+
+    # ---- nn.Module-ish surface the callers touch (builder.py:139-153) -----------------------------------------
+    def load_state_dict(self, state_dict, strict: bool = False):
+        self._eng.bind(state_dict)
+        return self
+
+    def eval(self):
+        return self
+
+    def requires_grad_(self, flag: bool = False):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    def cuda(self, *a, **k):
+        return self
+
+    def half(self):
+        return self
+
+    @property
+    def device(self):
+        return self._eng.tdev
+
+    @property
+    def dtype(self):
+        return torch.float16
+
+    def get_model(self):
+        return self
+
+    def get_vision_tower(self):
+        return self._tower
+
+    # ---- a2: encoders -------------------------------------------------------------------------------------------
+    def encode_images(self, images):
+        return self._eng.encode(0, images)
+
+    def encode_seg_images(self, seg_images):
+        return self._eng.encode(1, seg_images)
+
+    # ---- a5/a6: generate -------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def generate(self, input_ids=None, images=None, segs=None, depths=None, do_sample: bool = False,
+                 temperature: float = 1.0, top_p: Optional[float] = None, num_beams: int = 1,
+                 max_new_tokens: int = 20, use_cache: bool = True, streamer=None, stopping_criteria=None,
+                 attention_mask=None, eos_token_id=None, pad_token_id=None, **kwargs):
+        """Greedy `GenerationMixin.generate` semantics: returns cat([input_ids, new_ids]) on
+        input_ids' device; callers slice `[:, input_ids.shape[1]:]` (eval/model_depth_loader.py:170-174)."""
+        if input_ids is None:
+            raise ValueError("generate() needs input_ids")
+        if do_sample and temperature not in (0, 0.0):
+            raise NotImplementedError("sampling (do_sample=True) is SURVEY §8 row f1 ('next'); greedy only for now")
+        if num_beams != 1:
+            raise NotImplementedError("beam search is not on the reference's hot path (num_beams=1 everywhere)")
+        if attention_mask is not None and not bool(torch.as_tensor(attention_mask).bool().all()):
+            raise NotImplementedError("padded prompts: the reference itself mis-aligns the mask after the splice")
+        if self.variant == synth.VARIANT_VCODER and depths is not None:
+            raise TypeError("VCoderLlavaLlamaForCausalLM.generate() got an unexpected keyword argument 'depths'")
+        dev = input_ids.device
+        B = input_ids.shape[0]
+        interactive = streamer is not None or stopping_criteria is not None or eos_token_id is not None
+        try:
+            if not interactive:
+                new = self._eng.generate(input_ids, images, segs, depths, max_new_tokens=max_new_tokens)
+                return torch.cat([input_ids.to(dev), new.to(dev)], dim=1)
+            # token-by-token path: streamer / KeywordsStoppingCriteria (mm_utils.py:128-151) / eos need host ids
+            pre = self._eng.prefill(input_ids, images, segs, depths)
+            seq = torch.cat([input_ids.cpu(), pre["next_ids"].cpu().long()[:, None]], dim=1)
+            if streamer is not None:
+                streamer.put(input_ids.cpu())
+                streamer.put(seq[:, -1])
+            finished = torch.zeros(B, dtype=torch.bool)
+            for _ in range(max_new_tokens - 1):
+                if eos_token_id is not None:
+                    finished |= seq[:, -1] == eos_token_id
+                if bool(finished.all()):
+                    break
+                if stopping_criteria is not None and all(sc(seq, None) for sc in stopping_criteria):
+                    break
+                nxt = self._eng.decode(1).cpu().long()
+                if eos_token_id is not None and pad_token_id is not None:
+                    nxt[finished] = pad_token_id
+                seq = torch.cat([seq, nxt], dim=1)
+                if streamer is not None:
+                    streamer.put(nxt[:, 0])
+            if streamer is not None:
+                streamer.end()
+            return seq.to(dev)
+        except VcbError as e:
+            # same exception types the reference surfaces
+            if e.code == -6:
+                raise IndexError("index out of range in self") from e
+            if e.code == -5:
+                raise NameError("name '_new_labels' is not defined") from e
+            raise
+
+
+class VCoderDSLlavaLlamaForCausalLM(_VCoderBase):
+    """vcoder_ds_llava_llama.py:41 — RGB + seg + depth."""
+    variant = synth.VARIANT_VCODER_DS
+    model_type = "vcoder_ds_llava"
+
+    def encode_depth_images(self, depth_images):
+        return self._eng.encode(2, depth_images)  # seg_mm_projector, as the reference (vcoder_ds_llava_arch.py:113)
+
+
+class VCoderLlavaLlamaForCausalLM(_VCoderBase):
+    """vcoder_llava_llama.py:41 — RGB + seg."""
+    variant = synth.VARIANT_VCODER
+    model_type = "vcoder_llava"
+
+
+def build_model(model_name: str, g: ModelGeometry, state_dict=None, **kw):
+    """Class dispatch by substring of the model name, as load_pretrained_model does (builder.py:93-108)."""
+    name = model_name.lower()
+    if "vcoder_ds_llava" in name:
+        return VCoderDSLlavaLlamaForCausalLM(g, state_dict, **kw)
+    if "vcoder_llava" in name:
+        return VCoderLlavaLlamaForCausalLM(g, state_dict, **kw)
+    raise ValueError(f"{model_name}: only vcoder_llava / vcoder_ds_llava models are on the accelerated path")

@@ -47,7 +47,8 @@ class ModelGeometry:
     llm_rms_eps: float = 1e-5
     llm_rope_theta: float = 10000.0
     # init
-    init_gain: float = 1.0
+    init_gain: float = 1.0      # LLaMA-side std multiplier
+    vit_init_gain: float = 1.0  # CLIP-side std multiplier
 
     @property
     def n_patches(self) -> int:
@@ -78,7 +79,7 @@ _VT = "model.vision_tower.vision_tower.vision_model."
 def weight_specs(g: ModelGeometry):
     """[(name, shape, kind, std)]: kind in {'normal','ln_weight','bias'}. Names = reference state_dict keys."""
     d, f, L = g.vit_hidden, g.vit_ffn, g.vit_layers
-    k = g.init_gain
+    k = g.vit_init_gain
     specs = []
     # CLIPVisionEmbeddings (transformers/models/clip/modeling_clip.py:138-160); std as HF _init_weights
     specs.append((_VT + "embeddings.class_embedding", (d,), "normal", d ** -0.5))
@@ -118,7 +119,7 @@ def weight_specs(g: ModelGeometry):
         specs.append((f"model.{pj}.2.weight", (H, H), "normal", (H ** -0.5)))
         specs.append((f"model.{pj}.2.bias", (H,), "bias", 0.02))
     # LLaMA (HF init: N(0, 0.02^2); RMSNorm weight 1 — perturbed here so the scale path is exercised)
-    s = 0.02 * k
+    s = 0.02 * g.init_gain
     specs.append(("model.embed_tokens.weight", (g.llm_vocab, H), "normal", s))
     # vcoder_lm_emb is overwritten with a clone of embed_tokens on every prefill (vcoder_ds_llava_arch.py:173,
     # SURVEY F7): whatever the checkpoint holds is dead.  Generated with different values to prove it is ignored.
