@@ -2,7 +2,12 @@
 // Replaces HF eager attention at decode: softmax_fp32(q·K^T / sqrt(128)) · V over EVERY cached position — the
 // reference substitutes an all-ones mask of length past+1 on each decode step
 // (vcoder_llava/model/vcoder_ds_llava_arch.py:130-133; arithmetic modeling_llama.py:199-222).
-// HBM-bound: each K/V byte of the (b, head) stream is read once with 16-byte loads; 16 lanes cover one 128-dim row.
+//
+// HBM-bound (B·ctx·2·H·2 bytes per layer per step), so the kernel is organised around bytes in flight:
+// one CTA = (256-key split, head, sequence); a half-warp owns every 8th key of a 64-key page and its 16 lanes cover
+// one 128-dim row with 16-byte loads; per page each thread issues its 8 K-row and 8 V-row loads back to back (16
+// independent 16-byte loads in flight) and only then reduces.  Every half-warp runs its own online softmax, so the
+// main loop has no block-level synchronisation; the 8 partial (max, sum, acc) states are merged once through smem.
 #include "common.h"
 #include "kernels.h"
 #include "ptx.cuh"
@@ -11,6 +16,7 @@ namespace vcb {
 namespace {
 
 constexpr int kChunk = 256;  // keys per split
+constexpr int kPT = 64;      // tokens per KV page (checked on the host)
 constexpr int kDecThreads = 128;
 constexpr int kDH = 128;
 
@@ -18,14 +24,22 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
   float2 a = unpack_half2(u.x), b = unpack_half2(u.y), c = unpack_half2(u.z), d = unpack_half2(u.w);
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
+__device__ __forceinline__ uint4 ldg_stream16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
 
 __global__ void __launch_bounds__(kDecThreads)
 attn_decode_split_kernel(AttnDecodeParams p, int splits) {
-  __shared__ float s_p[kChunk];
-  __shared__ float s_red[8][kDH];
-  __shared__ float s_wred[4];
+  __shared__ float s_acc[8][kDH];
+  __shared__ float s_m[8], s_l[8];
+  griddep_launch();
+  griddep_wait();  // q and the current token's K/V row come from the kernels just before this one
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int tid = threadIdx.x, hw = tid >> 4, l16 = tid & 15, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, hw = tid >> 4, l16 = tid & 15;
   const int ctx = *p.ctx_len;
   const int k0 = split * kChunk;
   const long pidx = (static_cast<long>(b) * p.n_heads + h) * splits + split;
@@ -33,107 +47,95 @@ attn_decode_split_kernel(AttnDecodeParams p, int splits) {
     if (tid == 0) { p.part_ml[pidx * 2] = -INFINITY; p.part_ml[pidx * 2 + 1] = 0.f; }
     return;
   }
-  const int kend = min(k0 + kChunk, ctx);
-  const int nkeys = kend - k0;
+  const int nkeys = min(kChunk, ctx - k0);
 
   float qf[8];
   {
     const uint4 qv = *reinterpret_cast<const uint4*>(p.q + static_cast<long>(b) * p.q_stride + h * kDH + l16 * 8);
     unpack8(qv, qf);
-    const float sc = p.scale * 1.4426950408889634f;
+    const float sc = p.scale * 1.4426950408889634f;  // scores in the log2 domain
 #pragma unroll
     for (int i = 0; i < 8; ++i) qf[i] *= sc;
   }
-  const int32_t* bt = p.block_table + b * p.max_pages;
-  const int PT = p.page_tokens;
-  auto row_ptr = [&](const __half* pool, int key) -> const uint4* {
-    const int page = bt[key / PT];
-    const int slot = key % PT;
-    return reinterpret_cast<const uint4*>(pool + ((static_cast<long>(page) * p.n_heads + h) * PT + slot) * kDH + l16 * 8);
-  };
+  const int32_t* bt = p.block_table + b * p.max_pages + k0 / kPT;
 
-  // ---- phase 1: scores (log2 domain) -> smem
-  for (int base = 0; base < nkeys; base += 32) {  // warp-uniform trip count (shuffles inside)
-    const int kb = base + hw;
-    uint4 kv[4];
+  float m = -INFINITY, l = 0.f;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int ntiles = (nkeys + kPT - 1) / kPT;
+  for (int t = 0; t < ntiles; ++t) {
+    const long page_off = (static_cast<long>(bt[t]) * p.n_heads + h) * kPT * kDH + l16 * 8;
+    const __half* kb = p.k_pool + page_off;
+    const __half* vb = p.v_pool + page_off;
+    uint4 kv[8], vv[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int kk = kb + u * 8;
-      kv[u] = (kk < nkeys) ? __ldg(row_ptr(p.k_pool, k0 + kk)) : make_uint4(0, 0, 0, 0);
+    for (int i = 0; i < 8; ++i) {
+      const int slot = hw + 8 * i;
+      const bool ok = t * kPT + slot < nkeys;
+      kv[i] = ok ? ldg_stream16(kb + slot * kDH) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int i = 0; i < 8; ++i) {
+      const int slot = hw + 8 * i;
+      const bool ok = t * kPT + slot < nkeys;
+      vv[i] = ok ? ldg_stream16(vb + slot * kDH) : make_uint4(0, 0, 0, 0);
+    }
+    float s[8];
+    float mt = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
       float kf[8];
-      unpack8(kv[u], kf);
+      unpack8(kv[i], kf);
       float d = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) d = fmaf(qf[i], kf[i], d);
+      for (int e = 0; e < 8; ++e) d = fmaf(qf[e], kf[e], d);
       d += __shfl_xor_sync(0xffffffffu, d, 8);
       d += __shfl_xor_sync(0xffffffffu, d, 4);
       d += __shfl_xor_sync(0xffffffffu, d, 2);
       d += __shfl_xor_sync(0xffffffffu, d, 1);
-      const int kk = kb + u * 8;
-      if (l16 == 0 && kk < nkeys) s_p[kk] = d;
+      s[i] = (t * kPT + hw + 8 * i < nkeys) ? d : -INFINITY;
+      mt = fmaxf(mt, s[i]);
     }
-  }
-  __syncthreads();
-
-  // ---- phase 2: chunk max, probabilities, chunk sum
-  float m = -INFINITY;
-  for (int i = tid; i < nkeys; i += kDecThreads) m = fmaxf(m, s_p[i]);
+    const float m_new = fmaxf(m, mt);
+    const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+    const float corr = exp2f(m - m_use);  // m = -inf -> 0
+    l *= corr;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if (lane == 0) s_wred[warp] = m;
-  __syncthreads();
-  m = fmaxf(fmaxf(s_wred[0], s_wred[1]), fmaxf(s_wred[2], s_wred[3]));
-  __syncthreads();
-  float l = 0.f;
-  for (int i = tid; i < nkeys; i += kDecThreads) {
-    const float e = exp2f(s_p[i] - m);
-    s_p[i] = e;
-    l += e;
-  }
+    for (int e = 0; e < 8; ++e) acc[e] *= corr;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
-  if (lane == 0) s_wred[warp] = l;
-  __syncthreads();
-  l = s_wred[0] + s_wred[1] + s_wred[2] + s_wred[3];
-
-  // ---- phase 3: o = sum_k p_k V_k  (each half-warp takes every 8th key, lanes own 8 dims)
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int base = 0; base < nkeys; base += 32) {
-    const int kb = base + hw;
-    uint4 vv[4];
-    float pr[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int kk = kb + u * 8;
-      const bool ok = kk < nkeys;
-      vv[u] = ok ? __ldg(row_ptr(p.v_pool, k0 + kk)) : make_uint4(0, 0, 0, 0);
-      pr[u] = ok ? s_p[kk] : 0.f;
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int i = 0; i < 8; ++i) {
+      const float pr = exp2f(s[i] - m_use);  // masked -> 0
+      l += pr;
       float vf[8];
-      unpack8(vv[u], vf);
+      unpack8(vv[i], vf);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = fmaf(pr[u], vf[i], acc[i]);
+      for (int e = 0; e < 8; ++e) acc[e] = fmaf(pr, vf[e], acc[e]);
     }
+    m = m_new;
   }
+
+  // ---- merge the 8 half-warp states
 #pragma unroll
-  for (int i = 0; i < 8; ++i) s_red[hw][l16 * 8 + i] = acc[i];
+  for (int e = 0; e < 8; ++e) s_acc[hw][l16 * 8 + e] = acc[e];
+  if (l16 == 0) { s_m[hw] = m; s_l[hw] = l; }
   __syncthreads();
-  {
-    float v = 0.f;
+  float M = -INFINITY;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) v += s_red[w][tid];
-    p.part_o[pidx * kDH + tid] = v;
+  for (int w = 0; w < 8; ++w) M = fmaxf(M, s_m[w]);
+  float o = 0.f, L = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    const float wgt = (s_m[w] == -INFINITY) ? 0.f : exp2f(s_m[w] - M);
+    o += wgt * s_acc[w][tid];
+    L += wgt * s_l[w];
   }
-  if (tid == 0) { p.part_ml[pidx * 2] = m; p.part_ml[pidx * 2 + 1] = l; }
+  p.part_o[pidx * kDH + tid] = o;
+  if (tid == 0) { p.part_ml[pidx * 2] = M; p.part_ml[pidx * 2 + 1] = L; }
 }
 
 __global__ void __launch_bounds__(kDH)
 attn_decode_combine_kernel(AttnDecodeParams p, int splits) {
+  griddep_launch();
+  griddep_wait();
   const int bh = blockIdx.x;
   const int b = bh / p.n_heads, h = bh % p.n_heads;
   const int d = threadIdx.x;
@@ -158,12 +160,11 @@ int attn_decode_splits(int max_ctx) { return (max_ctx + kChunk - 1) / kChunk; }
 int attn_llama_decode(const AttnDecodeParams& p, cudaStream_t stream) {
   const int splits = attn_decode_splits(p.max_ctx);
   VCB_CHECK(splits >= 1, kErrInvalid, "attn_llama_decode: empty context");
+  VCB_CHECK(p.page_tokens == kPT, kErrInvalid, "attn_llama_decode: KV page must hold 64 tokens");
   dim3 grid(splits, p.n_heads, p.batch);
   KernelScope scope(kCatAttnDecode, stream, 2);
-  attn_decode_split_kernel<<<grid, kDecThreads, 0, stream>>>(p, splits);
-  VCB_CUDA(cudaGetLastError());
-  attn_decode_combine_kernel<<<p.batch * p.n_heads, kDH, 0, stream>>>(p, splits);
-  VCB_CUDA(cudaGetLastError());
+  VCB_CUDA(launch_pdl(attn_decode_split_kernel, grid, dim3(kDecThreads), 0, stream, p, splits));
+  VCB_CUDA(launch_pdl(attn_decode_combine_kernel, dim3(p.batch * p.n_heads), dim3(kDH), 0, stream, p, splits));
   return kOk;
 }
 

@@ -7,6 +7,9 @@
 // registers with warp-shuffle row reductions, K/V tiles staged through XOR-swizzled shared memory with a
 // double-buffered cp.async pipeline.  Scores never touch HBM: algorithmic traffic is Q,K,V in + O out.
 // (Round-1 version on the legacy HMMA path; the tcgen05/TMEM version is the next step — see DESIGN.md.)
+#include <cstdlib>
+#include <string>
+
 #include "common.h"
 #include "kernels.h"
 #include "ptx.cuh"
@@ -261,9 +264,20 @@ int launch_attn(const AttnPrefillParams& p, cudaStream_t stream) {
 
 }  // namespace
 
-int attn_vit(const AttnPrefillParams& p, cudaStream_t stream) {
+int attn_vit_legacy(const AttnPrefillParams& p, cudaStream_t stream) {
   VCB_CHECK(p.head_dim == 64, kErrInvalid, "attn_vit: head_dim must be 64");
   return launch_attn<64, false, false>(p, stream);
+}
+
+int attn_vit(const AttnPrefillParams& p, cudaStream_t stream) {
+  static int use_tc5 = -1;
+  if (use_tc5 < 0) {
+    const char* e = getenv("VCB_VIT_ATTN");
+    use_tc5 = (e != nullptr && std::string(e) == "tc5") ? 1 : 0;  // default stays on the verified kernel until tc5 is green
+  }
+  const bool packed = p.q_stride == p.kv_stride && p.k == p.q + p.n_heads * 64 && p.v == p.q + 2 * p.n_heads * 64;
+  if (use_tc5 && packed && p.seq_len <= 640 && p.q_stride % 8 == 0) return attn_vit_tc5(p, stream);
+  return attn_vit_legacy(p, stream);
 }
 
 int attn_llama_prefill(const AttnPrefillParams& p, cudaStream_t stream) {

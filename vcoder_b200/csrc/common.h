@@ -75,6 +75,24 @@ int gemm_f16(const __half* A, int lda, const __half* W, int ldw, int M, int N, i
 
 int device_sm_count();
 
+// Launch with the programmatic-stream-serialization (PDL) attribute; the kernel MUST call griddep_wait().
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // -------------------------------------------------------------------------------------------------
 // launch accounting / profiling (profile.cu)
 // -------------------------------------------------------------------------------------------------

@@ -118,6 +118,8 @@ constexpr int kRmsMaxChunks = 8;  // H <= 8192
 __global__ void __launch_bounds__(kRmsThreads)
 rmsnorm_kernel(const __half* __restrict__ x, const __half* __restrict__ w, __half* __restrict__ y, int H, float eps) {
   __shared__ float scratch[kRmsThreads / 32];
+  griddep_launch();
+  griddep_wait();
   const long row = blockIdx.x;
   const int nch = H / 8;
   const uint4* xr = reinterpret_cast<const uint4*>(x + row * H);
@@ -153,6 +155,8 @@ rmsnorm_kernel(const __half* __restrict__ x, const __half* __restrict__ w, __hal
 __global__ void rope_kv_kernel(__half* qkv, int T, int H, int n_heads, const float2* __restrict__ cs, int pos0,
                                const int32_t* __restrict__ pos0_dev, __half* k_pool, __half* v_pool,
                                const int32_t* __restrict__ block_table, int max_pages, int PT) {
+  griddep_launch();
+  griddep_wait();
   const long m = blockIdx.x;
   const int b = static_cast<int>(m / T), tt = static_cast<int>(m % T);
   const int pos = (pos0_dev ? *pos0_dev : pos0) + tt;
@@ -218,6 +222,8 @@ __global__ void splice_gather_kernel(const int32_t* __restrict__ plan, const __h
 
 __global__ void embed_gather_kernel(const int32_t* __restrict__ ids, const __half* __restrict__ embed,
                                     __half* __restrict__ out, int H) {
+  griddep_launch();
+  griddep_wait();
   const int b = blockIdx.x;
   const uint4* s = reinterpret_cast<const uint4*>(embed + static_cast<long>(ids[b]) * H);
   uint4* o = reinterpret_cast<uint4*>(out + static_cast<long>(b) * H);
@@ -231,6 +237,8 @@ argmax_kernel(const __half* __restrict__ logits, int V, int32_t* next, int32_t* 
               const int32_t* __restrict__ step_dev) {
   __shared__ float s_v[kArgThreads / 32];
   __shared__ int s_i[kArgThreads / 32];
+  griddep_launch();
+  griddep_wait();
   const int b = blockIdx.x;
   const __half* row = logits + static_cast<long>(b) * V;
   float best = -INFINITY;
@@ -267,6 +275,8 @@ __global__ void compact_patches_kernel(const __half* __restrict__ hidden, __half
 
 // counters: [0] cache_len (= position of the token being decoded), [1] tokens produced, [2] cache_len + 1
 __global__ void advance_kernel(int32_t* counters) {
+  griddep_launch();
+  griddep_wait();
   if (threadIdx.x == 0) { counters[0] += 1; counters[1] += 1; counters[2] += 1; }
 }
 
@@ -300,8 +310,7 @@ int layernorm_f16(const __half* x, const __half* w, const __half* b, __half* y, 
 int rmsnorm_f16(const __half* x, const __half* w, __half* y, long rows, int H, float eps, cudaStream_t s) {
   VCB_CHECK(H % 8 == 0 && H <= kRmsMaxChunks * kRmsThreads * 8, kErrInvalid, "rmsnorm_f16: H must be <= 8192, % 8");
   KernelScope scope(kCatNorm, s);
-  rmsnorm_kernel<<<static_cast<unsigned>(rows), kRmsThreads, 0, s>>>(x, w, y, H, eps);
-  VCB_CUDA(cudaGetLastError());
+  VCB_CUDA(launch_pdl(rmsnorm_kernel, dim3(static_cast<unsigned>(rows)), dim3(kRmsThreads), 0, s, x, w, y, H, eps));
   return kOk;
 }
 
@@ -311,9 +320,8 @@ int rope_kv_write(__half* qkv, int B, int T, int H, int n_heads, const float2* c
   VCB_CHECK(H == n_heads * 128, kErrInvalid, "rope_kv_write: head_dim must be 128");
   const int threads = std::min(256, n_heads * 8);
   KernelScope scope(kCatRope, s);
-  rope_kv_kernel<<<static_cast<unsigned>(static_cast<long>(B) * T), threads, 0, s>>>(
-      qkv, T, H, n_heads, cos_sin, pos0, pos0_dev, k_pool, v_pool, block_table, max_pages, page_tokens);
-  VCB_CUDA(cudaGetLastError());
+  VCB_CUDA(launch_pdl(rope_kv_kernel, dim3(static_cast<unsigned>(static_cast<long>(B) * T)), dim3(threads), 0, s, qkv, T, H,
+                      n_heads, cos_sin, pos0, pos0_dev, k_pool, v_pool, block_table, max_pages, page_tokens));
   return kOk;
 }
 
@@ -327,16 +335,14 @@ int splice_gather(const int32_t* plan, const __half* embed, const __half* feats,
 
 int embed_gather(const int32_t* ids, const __half* embed, __half* out, int B, int H, cudaStream_t s) {
   KernelScope scope(kCatMisc, s);
-  embed_gather_kernel<<<B, 128, 0, s>>>(ids, embed, out, H);
-  VCB_CUDA(cudaGetLastError());
+  VCB_CUDA(launch_pdl(embed_gather_kernel, dim3(B), dim3(128), 0, s, ids, embed, out, H));
   return kOk;
 }
 
 int argmax_rows(const __half* logits, int B, int V, int32_t* next, int32_t* trace, int trace_stride,
                 const int32_t* step_dev, cudaStream_t s) {
   KernelScope scope(kCatMisc, s);
-  argmax_kernel<<<B, kArgThreads, 0, s>>>(logits, V, next, trace, trace_stride, step_dev);
-  VCB_CUDA(cudaGetLastError());
+  VCB_CUDA(launch_pdl(argmax_kernel, dim3(B), dim3(kArgThreads), 0, s, logits, V, next, trace, trace_stride, step_dev));
   return kOk;
 }
 
@@ -350,8 +356,7 @@ int compact_patches(const __half* hidden, __half* out, int B, int tokens, int D,
 
 int advance_counters(int32_t* counters, cudaStream_t s) {
   KernelScope scope(kCatMisc, s);
-  advance_kernel<<<1, 32, 0, s>>>(counters);
-  VCB_CUDA(cudaGetLastError());
+  VCB_CUDA(launch_pdl(advance_kernel, dim3(1), dim3(32), 0, s, counters));
   return kOk;
 }
 

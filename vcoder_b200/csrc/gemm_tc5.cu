@@ -286,6 +286,25 @@ int launch_act(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpilogu
 
 }  // namespace
 
+// generic 2-D fp16 tensor map with the 128-byte swizzle (box_inner must be 64 elements = 128 bytes)
+int make_tmap_2d_f16(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows, uint64_t ld_elems, uint32_t box_inner,
+                     uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  VCB_CHECK(fn != nullptr, kErrCuda, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_thread_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
+    return kErrCuda;
+  }
+  return kOk;
+}
+
 int device_sm_count() {
   static int n = 0;
   if (n == 0) {

@@ -23,7 +23,9 @@ struct AttnPrefillParams {
   int batch = 0, n_heads = 0, seq_len = 0, head_dim = 0;
   float scale = 1.f;
 };
-int attn_vit(const AttnPrefillParams& p, cudaStream_t stream);
+int attn_vit(const AttnPrefillParams& p, cudaStream_t stream);       // dispatcher: tcgen05 kernel when it applies
+int attn_vit_tc5(const AttnPrefillParams& p, cudaStream_t stream);   // tcgen05 + TMEM (attn_vit_tc5.cu)
+int attn_vit_legacy(const AttnPrefillParams& p, cudaStream_t stream);  // mma.sync flash attention
 int attn_llama_prefill(const AttnPrefillParams& p, cudaStream_t stream);
 
 struct AttnDecodeParams {
@@ -55,6 +57,7 @@ struct SkinnyParams {
   long ldr = 0;
   int B = 0, N = 0, K = 0;
   int swiglu = 0;  // W rows 8/8 interleaved gate|up; N_out = N/2
+  int mode = 1;    // chunk->warp mapping (see skinny.cu)
 };
 int skinny_gemm(const SkinnyParams& p, cudaStream_t stream);
 

@@ -1,6 +1,7 @@
 // Launch accounting and optional per-kernel-category timing (CUDA events on the launching stream).
 // bench.py uses it for `gpu_launches` and for the live roofline numbers of the dominant kernel.
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -23,6 +24,12 @@ cudaEvent_t get_event() {
   return e;
 }
 }  // namespace
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("VCB_PDL"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
 
 uint64_t launch_count() { return g_launches.load(); }
 void launch_count_add(int64_t n) { g_launches.fetch_add(static_cast<uint64_t>(n)); }

@@ -31,6 +31,14 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ---------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization attribute may start
+// while its predecessor drains; it must execute griddep_wait() before touching anything the predecessor wrote
+// (or writing anything the predecessor may still read).  griddep_launch() lets OUR dependents start early.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {

@@ -7,13 +7,18 @@
 // K-permutation trick: a dot product is invariant under any permutation of k applied to both operands, so each
 // thread loads 8 CONTIGUOUS halves of a W row (one LDG.128) and of an X row and feeds them to two MMAs as if they
 // were the strided fragment elements the instruction expects.
+//
+// Programmatic dependent launch: the kernel starts while its predecessor drains, issues its first weight loads
+// (weights never depend on the predecessor), and only then waits on the grid dependency before touching X — so the
+// HBM stream does not stop at kernel boundaries.
+#include <cstdlib>
+
 #include "common.h"
 #include "kernels.h"
 #include "ptx.cuh"
 
 namespace vcb {
 namespace {
-
 
 __device__ __forceinline__ uint4 ldg_stream(const void* p) {
   uint4 r;
@@ -31,19 +36,50 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a
 }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
+constexpr int U = 4;  // 32-wide k chunks per batch of loads: 8 independent 16-byte weight loads per thread
+
 // WARPS = split-K factor inside the CTA: small-N problems use more warps per 16-row tile so that enough
 // 16-byte loads are in flight per SM to cover HBM latency.
 template <int NB, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 skinny_gemm_kernel(SkinnyParams p) {
-  constexpr int kSkWarps = WARPS;
-  constexpr int kSkThreads = WARPS * 32;
-  __shared__ float red[kSkWarps][16][8 * NB + 1];
+  constexpr int kThreads = WARPS * 32;
+  __shared__ float red[WARPS][16][8 * NB + 1];
+  griddep_launch();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int row0 = blockIdx.x * 16;
   const __half* w_lo = p.W + static_cast<long>(row0 + g) * p.K + t * 8;
   const __half* w_hi = w_lo + 8L * p.K;
+
+  // chunk -> warp mapping: mode 0 interleaves 64-byte chunks over the warps of the CTA; mode 1 gives every warp one
+  // contiguous k-range so a warp streams each of its 16 rows sequentially (U*64 contiguous bytes per row per batch)
+  const int n_chunks = p.K / 32;
+  int c, c_end, c_step;
+  if (p.mode == 0) {
+    c = warp; c_end = n_chunks; c_step = WARPS;
+  } else {
+    const int per = (n_chunks + WARPS - 1) / WARPS;
+    c = warp * per; c_end = min(n_chunks, c + per); c_step = 1;
+  }
+  auto load_w = [&](int cc, uint4 (&wl)[U], uint4 (&wh)[U]) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int ch = cc + u * c_step;
+      if (ch < c_end) {
+        wl[u] = ldg_stream(w_lo + ch * 32);
+        wh[u] = ldg_stream(w_hi + ch * 32);
+      } else {
+        wl[u] = make_uint4(0, 0, 0, 0);
+        wh[u] = make_uint4(0, 0, 0, 0);
+      }
+    }
+  };
+
+  uint4 wl[U], wh[U];
+  load_w(c, wl, wh);   // weights do not depend on the previous kernel: start streaming before the dependency wait
+  griddep_wait();      // X (and the residual) are produced by the previous kernel in the stream
+
   const __half* xrow[NB];
   bool xok[NB];
 #pragma unroll
@@ -55,25 +91,19 @@ skinny_gemm_kernel(SkinnyParams p) {
 #pragma unroll
   for (int nb = 0; nb < NB; ++nb) { acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f; }
 
-  const int n_chunks = p.K / 32;
-  constexpr int U = 4;  // chunks in flight per warp iteration: 8 independent 16-byte weight loads per thread
-  int c = warp;
-  for (; c + (U - 1) * kSkWarps < n_chunks; c += U * kSkWarps) {
-    uint4 wl[U], wh[U], xv[U][NB];
+  for (; c < c_end; c += U * c_step) {
+    uint4 xv[U][NB];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int k0 = (c + u * kSkWarps) * 32;
-      wl[u] = ldg_stream(w_lo + k0);
-      wh[u] = ldg_stream(w_hi + k0);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int k0 = (c + u * kSkWarps) * 32;
+      const int ch = c + u * c_step;
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb) {
-        xv[u][nb] = xok[nb] ? __ldg(reinterpret_cast<const uint4*>(xrow[nb] + k0)) : make_uint4(0, 0, 0, 0);
+        xv[u][nb] = (xok[nb] && ch < c_end) ? __ldg(reinterpret_cast<const uint4*>(xrow[nb] + ch * 32))
+                                             : make_uint4(0, 0, 0, 0);
       }
     }
+    uint4 nl[U], nh[U];  // next batch of weights in flight while this one is multiplied
+    load_w(c + U * c_step, nl, nh);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
 #pragma unroll
@@ -82,17 +112,8 @@ skinny_gemm_kernel(SkinnyParams p) {
         mma_16816(acc[nb], wl[u].z, wh[u].z, wl[u].w, wh[u].w, xv[u][nb].z, xv[u][nb].w);
       }
     }
-  }
-  for (; c < n_chunks; c += kSkWarps) {
-    const int k0 = c * 32;
-    const uint4 wl = ldg_stream(w_lo + k0);
-    const uint4 wh = ldg_stream(w_hi + k0);
 #pragma unroll
-    for (int nb = 0; nb < NB; ++nb) {
-      const uint4 xv = xok[nb] ? __ldg(reinterpret_cast<const uint4*>(xrow[nb] + k0)) : make_uint4(0, 0, 0, 0);
-      mma_16816(acc[nb], wl.x, wh.x, wl.y, wh.y, xv.x, xv.y);
-      mma_16816(acc[nb], wl.z, wh.z, wl.w, wh.w, xv.z, xv.w);
-    }
+    for (int u = 0; u < U; ++u) { wl[u] = nl[u]; wh[u] = nh[u]; }
   }
 
   // cross-warp (split-K) reduction through shared memory
@@ -105,27 +126,39 @@ skinny_gemm_kernel(SkinnyParams p) {
   }
   __syncthreads();
   if (p.swiglu) {
-    for (int idx = tid; idx < 8 * 8 * NB; idx += kSkThreads) {
+    for (int idx = tid; idx < 8 * 8 * NB; idx += kThreads) {
       const int e = idx & 7, n = idx >> 3;
       if (n < p.B) {
         float gate = 0.f, up = 0.f;
 #pragma unroll
-        for (int w = 0; w < kSkWarps; ++w) { gate += red[w][e][n]; up += red[w][e + 8][n]; }
+        for (int w = 0; w < WARPS; ++w) { gate += red[w][e][n]; up += red[w][e + 8][n]; }
         p.Y[static_cast<long>(n) * p.ldy + blockIdx.x * 8 + e] = __float2half_rn(silu_f(gate) * up);
       }
     }
   } else {
-    for (int idx = tid; idx < 16 * 8 * NB; idx += kSkThreads) {
+    for (int idx = tid; idx < 16 * 8 * NB; idx += kThreads) {
       const int r = idx & 15, n = idx >> 4;
       if (n < p.B) {
         float v = 0.f;
 #pragma unroll
-        for (int w = 0; w < kSkWarps; ++w) v += red[w][r][n];
+        for (int w = 0; w < WARPS; ++w) v += red[w][r][n];
         if (p.residual) v += __half2float(p.residual[static_cast<long>(n) * p.ldr + row0 + r]);
         p.Y[static_cast<long>(n) * p.ldy + row0 + r] = __float2half_rn(v);
       }
     }
   }
+}
+
+template <int NB, int WARPS>
+int launch_sk(const SkinnyParams& p, int grid, cudaStream_t stream) {
+  VCB_CUDA(launch_pdl(skinny_gemm_kernel<NB, WARPS>, dim3(grid), dim3(WARPS * 32), 0, stream, p));
+  return kOk;
+}
+template <int NB>
+int launch_sk_w(const SkinnyParams& p, int grid, int warps, cudaStream_t stream) {
+  if (warps == 16) return launch_sk<NB, 16>(p, grid, stream);
+  if (warps == 8) return launch_sk<NB, 8>(p, grid, stream);
+  return launch_sk<NB, 4>(p, grid, stream);
 }
 
 }  // namespace
@@ -139,24 +172,19 @@ int skinny_gemm(const SkinnyParams& p, cudaStream_t stream) {
   const int nb = (p.B + 7) / 8;
   // aim for >= ~32 resident warps per SM
   const int warps = grid <= 512 ? 16 : (grid <= 1024 ? 8 : 4);
-  KernelScope scope(kCatSkinny, stream);
-#define VCB_SK(NB_, W_) skinny_gemm_kernel<NB_, W_><<<grid, W_ * 32, 0, stream>>>(p)
-#define VCB_SKW(NB_)                                     \
-  do {                                                   \
-    if (warps == 16) VCB_SK(NB_, 16);                    \
-    else if (warps == 8) VCB_SK(NB_, 8);                 \
-    else VCB_SK(NB_, 4);                                 \
-  } while (0)
-  switch (nb) {
-    case 1: VCB_SKW(1); break;
-    case 2: VCB_SKW(2); break;
-    case 3: VCB_SKW(3); break;
-    default: VCB_SKW(4); break;
+  SkinnyParams pp = p;
+  {
+    static int env_mode = -1;
+    if (env_mode < 0) { const char* e = getenv("VCB_SKINNY_MODE"); env_mode = e ? atoi(e) : 1; }
+    pp.mode = env_mode;
   }
-#undef VCB_SKW
-#undef VCB_SK
-  VCB_CUDA(cudaGetLastError());
-  return kOk;
+  KernelScope scope(kCatSkinny, stream);
+  switch (nb) {
+    case 1: return launch_sk_w<1>(pp, grid, warps, stream);
+    case 2: return launch_sk_w<2>(pp, grid, warps, stream);
+    case 3: return launch_sk_w<3>(pp, grid, warps, stream);
+    default: return launch_sk_w<4>(pp, grid, warps, stream);
+  }
 }
 
 }  // namespace vcb
