@@ -106,6 +106,13 @@ int vcb_op_skinny_gemm_f16(const vcb_half* X_dev, int32_t ldx, const vcb_half* W
                            const vcb_half* residual_dev, int32_t ldr, int32_t swiglu, vcb_half* Y_dev, int32_t ldy,
                            void* stream);
 
+/* Same kernel with LlamaRMSNorm fused onto X (decode path): Y = rsqrt(mean(x^2)+eps) * ((x o norm_w) · W^T) (+ residual).
+ * Replaces `self.input_layernorm` / `post_attention_layernorm` / `model.norm` followed by the Linear
+ * (transformers/models/llama/modeling_llama.py:53-70, 171-184). */
+int vcb_op_skinny_rmsnorm_gemm_f16(const vcb_half* X_dev, int32_t ldx, const vcb_half* norm_w_dev, float eps,
+                                   const vcb_half* W_dev, int32_t B, int32_t N, int32_t K, const vcb_half* residual_dev,
+                                   int32_t ldr, int32_t swiglu, vcb_half* Y_dev, int32_t ldy, void* stream);
+
 /* nn.LayerNorm over the last dim (CLIP pre_layrnorm / layer_norm1/2), rows x D fp16. */
 int vcb_op_layernorm_f16(const vcb_half* x_dev, const vcb_half* w_dev, const vcb_half* b_dev, vcb_half* y_dev,
                          int64_t rows, int32_t D, float eps, void* stream);

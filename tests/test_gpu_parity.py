@@ -106,6 +106,25 @@ def test_skinny_gemm(B, N, K, sw, res):
     assert_close_kernel(Y, ref, f"skinny {B}x{N}x{K}")
 
 
+@pytest.mark.parametrize("B,N,K,sw", [(8, 12288, 4096, 0), (8, 1024, 512, 1), (5, 512, 256, 0), (16, 32000, 4096, 0)])
+def test_skinny_gemm_fused_rmsnorm(B, N, K, sw):
+    lib = _lib.load()
+    torch.manual_seed(B * N)
+    X = (torch.randn(B, K, device=DEV) * 1.7).half()
+    wn = (1 + 0.1 * torch.randn(K, device=DEV)).half()
+    W = (torch.randn(N, K, device=DEV) * 0.03).half()
+    No = N // 2 if sw else N
+    Y = torch.full((B, No), float("nan"), device=DEV, dtype=torch.float16)
+    _lib.check(lib.vcb_op_skinny_rmsnorm_gemm_f16(_lib.ptr(X), K, _lib.ptr(wn), 1e-5, _lib.ptr(W), B, N, K, None, N, sw,
+                                                  _lib.ptr(Y), No, ST))
+    torch.cuda.synchronize()
+    ref = orc.rms_norm(X.float().cpu(), wn.float().cpu(), 1e-5) @ W.float().cpu().t()
+    if sw:
+        r = ref.view(B, N // 16, 2, 8)
+        ref = (torch.nn.functional.silu(r[:, :, 0]) * r[:, :, 1]).reshape(B, N // 2)
+    assert rel_rms(Y, ref) <= 6e-4 and max_abs(Y, ref) <= 3 * ulp16(float(ref.abs().max())), (rel_rms(Y, ref), max_abs(Y, ref))
+
+
 def test_norms():
     lib = _lib.load()
     torch.manual_seed(1)

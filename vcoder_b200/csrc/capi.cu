@@ -80,6 +80,17 @@ int vcb_op_skinny_gemm_f16(const vcb_half* X, int32_t ldx, const vcb_half* W, in
   return skinny_gemm(s, ST(stream));
 }
 
+int vcb_op_skinny_rmsnorm_gemm_f16(const vcb_half* X, int32_t ldx, const vcb_half* norm_w, float eps, const vcb_half* W,
+                                   int32_t B, int32_t N, int32_t K, const vcb_half* residual, int32_t ldr, int32_t swiglu,
+                                   vcb_half* Y, int32_t ldy, void* stream) {
+  VCB_TRY(require_device());
+  VCB_CHECK(norm_w != nullptr, kErrInvalid, "vcb_op_skinny_rmsnorm_gemm_f16: norm_w is null");
+  SkinnyParams s;
+  s.X = H(X); s.ldx = ldx; s.W = H(W); s.Y = H(Y); s.ldy = ldy; s.residual = H(residual); s.ldr = ldr;
+  s.B = B; s.N = N; s.K = K; s.swiglu = swiglu; s.norm_w = H(norm_w); s.norm_eps = eps;
+  return skinny_gemm(s, ST(stream));
+}
+
 int vcb_op_layernorm_f16(const vcb_half* x, const vcb_half* w, const vcb_half* b, vcb_half* y, int64_t rows, int32_t D,
                          float eps, void* stream) {
   VCB_TRY(require_device());

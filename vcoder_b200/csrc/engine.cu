@@ -635,10 +635,10 @@ int engine_prefill(Engine* e, const int64_t* ids, int B, int T, const void* imag
   __half* xd = e->xd.as<__half>();
   VCB_CUDA(cudaMemcpy2DAsync(xd, H * 2, x + static_cast<long>(Tp - 1) * H, static_cast<size_t>(Tp) * H * 2, H * 2, B,
                              cudaMemcpyDeviceToDevice, st));
-  VCB_TRY(rmsnorm_f16(xd, e->final_norm.as<__half>(), e->xnd.as<__half>(), B, H, c.llm_rms_eps, st));
   {
-    SkinnyParams s;
-    s.X = e->xnd.as<__half>(); s.ldx = H; s.W = e->lm_head.as<__half>(); s.Y = e->logits.as<__half>(); s.ldy = V;
+    SkinnyParams s;  // final RMSNorm fused into the lm_head GEMM
+    s.norm_w = e->final_norm.as<__half>(); s.norm_eps = c.llm_rms_eps;
+    s.X = xd; s.ldx = H; s.W = e->lm_head.as<__half>(); s.Y = e->logits.as<__half>(); s.ldy = V;
     s.B = B; s.N = V; s.K = H;
     VCB_TRY(skinny_gemm(s, st));
   }

@@ -58,6 +58,11 @@ struct SkinnyParams {
   int B = 0, N = 0, K = 0;
   int swiglu = 0;  // W rows 8/8 interleaved gate|up; N_out = N/2
   int mode = 1;    // chunk->warp mapping (see skinny.cu)
+  int prefetch = 0;  // cp.async.bulk.prefetch.L2 ahead of the demand loads (measured slower: off)
+  int double_buffer = 0;  // keep the next batch of weight loads in flight during the MMAs (costs registers)
+  // fused LlamaRMSNorm on X (decode): Y = rsqrt(mean(x^2)+eps) * W (x o norm_w); null = X is used as is
+  const __half* norm_w = nullptr;
+  float norm_eps = 0.f;
 };
 int skinny_gemm(const SkinnyParams& p, cudaStream_t stream);
 

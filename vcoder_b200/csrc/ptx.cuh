@@ -203,6 +203,12 @@ __host__ __device__ constexpr uint32_t make_idesc_f16_bmn(int m, int n) {
 // ---------------------------------------------------------------------------------------------
 // small math helpers
 // ---------------------------------------------------------------------------------------------
+// raw MUFU exp2 (ex2.approx.ftz): 2 ulp, flushes denormals, exp2(-inf) = 0
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);

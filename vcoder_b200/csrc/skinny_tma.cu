@@ -1,0 +1,200 @@
+// TMA-fed variant of the weight-streaming skinny GEMM (decode / lm_head):  Y[B,N] = X[B,K] · W[N,K]^T,  B <= 32.
+// Same math and the same K-permutation MMA trick as skinny.cu, but the weight stream is driven by the TMA engine:
+// every warp owns a K-range of the CTA's 16-row tile and keeps a ring of kDepth bulk-tensor loads in flight
+// ([4 k-blocks][16 rows][64 k] = 8 KiB each, 128B-swizzled so the fragment reads are bank-conflict free).  The bytes
+// in flight per SM (up to ~190 KiB) no longer depend on registers or on L1 miss slots, which is what the plain-LDG
+// kernel runs out of.  Programmatic dependent launch: ring fill happens BEFORE the grid-dependency wait — weights do
+// not depend on the previous kernel, so HBM keeps streaming across kernel boundaries.
+#include <cstdlib>
+
+#include "common.h"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace vcb {
+namespace {
+
+constexpr int kKBlk = 64;               // k elements per 128-byte swizzled row
+constexpr int kGroup = 4;               // k-blocks per TMA box
+constexpr int kStageBytes = kGroup * 16 * kKBlk * 2;  // 8 KiB
+constexpr int kDepth = 3;               // stages in flight per warp
+
+__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                          uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + fast_exp2(-1.4426950408889634f * x)); }
+
+// W viewed as a 3-D tensor [K/64][N][64]: dim0 = k within a 64-block, dim1 = row, dim2 = k-block
+template <int NB, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+skinny_tma_kernel(const __grid_constant__ CUtensorMap tmW, SkinnyParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];  // [WARPS][kDepth] stages | red | barriers (no static smem: base stays 1 KiB aligned)
+  typedef float RedT[16][8 * NB + 1];
+  RedT* red = reinterpret_cast<RedT*>(smem + WARPS * kDepth * kStageBytes);
+  typedef uint64_t BarT[kDepth];
+  BarT* bars = reinterpret_cast<BarT*>(smem + WARPS * kDepth * kStageBytes + sizeof(RedT) * WARPS + 8);
+  griddep_launch();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int row0 = blockIdx.x * 16;
+  const uint32_t ring = smem_u32(smem) + warp * (kDepth * kStageBytes);
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+
+  // this warp's range of k-groups (a group = 4 k-blocks = 256 k)
+  const int n_groups = (p.K / kKBlk + kGroup - 1) / kGroup;
+  const int per = (n_groups + WARPS - 1) / WARPS;
+  const int g_begin = min(n_groups, warp * per), g_end = min(n_groups, g_begin + per);
+  const int my_groups = g_end - g_begin;
+
+  if (lane == 0) {
+    for (int s = 0; s < kDepth; ++s) mbar_init(smem_u32(&bars[warp][s]), 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < kDepth && s < my_groups; ++s) {  // fill the ring before waiting on the previous kernel
+      const uint32_t b = smem_u32(&bars[warp][s]);
+      mbar_expect_tx(b, kStageBytes);
+      tma_load_3d(ring + s * kStageBytes, &tmW, b, 0, row0, (g_begin + s) * kGroup);
+    }
+  }
+  __syncwarp();
+  griddep_wait();  // X (and the residual) come from the previous kernel
+
+  const __half* xrow[NB];
+  bool xok[NB];
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb) {
+    xok[nb] = (nb * 8 + g) < p.B;
+    xrow[nb] = p.X + static_cast<long>(xok[nb] ? nb * 8 + g : 0) * p.ldx + t * 8;
+  }
+  float acc[NB][4];
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb) { acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f; }
+
+  const uint32_t r_lo = static_cast<uint32_t>(g) * 128, r_hi = static_cast<uint32_t>(g + 8) * 128;
+  for (int i = 0; i < my_groups; ++i) {
+    const int s = i % kDepth;
+    const uint32_t ph = static_cast<uint32_t>((i / kDepth) & 1);
+    const int k0 = (g_begin + i) * kGroup * kKBlk;
+    // X for the 8 32-k chunks of this group (issued before the barrier wait so they overlap it)
+    uint4 xv[2 * kGroup][NB];
+#pragma unroll
+    for (int c = 0; c < 2 * kGroup; ++c) {
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        const int k = k0 + c * 32;
+        xv[c][nb] = (xok[nb] && k < p.K) ? __ldg(reinterpret_cast<const uint4*>(xrow[nb] + k)) : make_uint4(0, 0, 0, 0);
+      }
+    }
+    mbar_wait(smem_u32(&bars[warp][s]), ph);
+    const uint32_t st = ring + s * kStageBytes;
+#pragma unroll
+    for (int kb = 0; kb < kGroup; ++kb) {
+#pragma unroll
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        // 32-k chunk (kb, hlf): thread t takes 16-byte chunk 4*hlf + t of rows g and g+8 (swizzle: chunk ^ (row & 7))
+        const uint32_t ch = static_cast<uint32_t>(4 * hlf + t);
+        const uint4 wl = lds128(st + kb * 2048 + r_lo + ((ch ^ static_cast<uint32_t>(g & 7)) << 4));
+        const uint4 wh = lds128(st + kb * 2048 + r_hi + ((ch ^ static_cast<uint32_t>((g + 8) & 7)) << 4));
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+          const uint4 x = xv[kb * 2 + hlf][nb];
+          mma_16816(acc[nb], wl.x, wh.x, wl.y, wh.y, x.x, x.y);
+          mma_16816(acc[nb], wl.z, wh.z, wl.w, wh.w, x.z, x.w);
+        }
+      }
+    }
+    __syncwarp();  // every lane is done with stage s before it is refilled
+    if (lane == 0 && i + kDepth < my_groups) {
+      const uint32_t b = smem_u32(&bars[warp][s]);
+      mbar_expect_tx(b, kStageBytes);
+      tma_load_3d(st, &tmW, b, 0, row0, (g_begin + i + kDepth) * kGroup);
+    }
+  }
+
+  // cross-warp (split-K) reduction through shared memory
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb) {
+    red[warp][g][nb * 8 + 2 * t] = acc[nb][0];
+    red[warp][g][nb * 8 + 2 * t + 1] = acc[nb][1];
+    red[warp][g + 8][nb * 8 + 2 * t] = acc[nb][2];
+    red[warp][g + 8][nb * 8 + 2 * t + 1] = acc[nb][3];
+  }
+  __syncthreads();
+  constexpr int kThreads = WARPS * 32;
+  if (p.swiglu) {
+    for (int idx = tid; idx < 8 * 8 * NB; idx += kThreads) {
+      const int e = idx & 7, n = idx >> 3;
+      if (n < p.B) {
+        float gate = 0.f, up = 0.f;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) { gate += red[w][e][n]; up += red[w][e + 8][n]; }
+        p.Y[static_cast<long>(n) * p.ldy + blockIdx.x * 8 + e] = __float2half_rn(silu_f(gate) * up);
+      }
+    }
+  } else {
+    for (int idx = tid; idx < 16 * 8 * NB; idx += kThreads) {
+      const int r = idx & 15, n = idx >> 4;
+      if (n < p.B) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) v += red[w][r][n];
+        if (p.residual) v += __half2float(p.residual[static_cast<long>(n) * p.ldr + row0 + r]);
+        p.Y[static_cast<long>(n) * p.ldy + row0 + r] = __float2half_rn(v);
+      }
+    }
+  }
+}
+
+template <int NB, int WARPS>
+int launch_tma(const CUtensorMap& tm, const SkinnyParams& p, int grid, cudaStream_t stream) {
+  constexpr int smem = WARPS * kDepth * kStageBytes + WARPS * 16 * (8 * NB + 1) * 4 + 8 + WARPS * kDepth * 8 + 16;
+  static bool attr = false;
+  if (!attr) {
+    VCB_CUDA(cudaFuncSetAttribute(skinny_tma_kernel<NB, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  VCB_CUDA(launch_pdl(skinny_tma_kernel<NB, WARPS>, dim3(grid), dim3(WARPS * 32), smem, stream, tm, p));
+  return kOk;
+}
+template <int NB>
+int launch_tma_w(const CUtensorMap& tm, const SkinnyParams& p, int grid, int warps, cudaStream_t stream) {
+  if (warps >= 8) return launch_tma<NB, 8>(tm, p, grid, stream);
+  if (warps >= 4) return launch_tma<NB, 4>(tm, p, grid, stream);
+  return launch_tma<NB, 2>(tm, p, grid, stream);
+}
+
+}  // namespace
+
+int make_tmap_w3d(CUtensorMap* m, const void* ptr, uint64_t K, uint64_t N);
+
+int skinny_gemm_tma(const SkinnyParams& p, cudaStream_t stream) {
+  VCB_CHECK(p.B >= 1 && p.B <= 32, kErrInvalid, "skinny_gemm: batch must be in [1, 32]");
+  VCB_CHECK(p.N % 16 == 0 && p.K % 64 == 0, kErrInvalid, "skinny_gemm_tma: N % 16 and K % 64 must be 0");
+  VCB_CHECK(p.norm_w == nullptr, kErrInvalid, "skinny_gemm_tma: fused norm is only in the LDG kernel");
+  const int grid = p.N / 16;
+  const int nb = (p.B + 7) / 8;
+  int warps = 4;  // 4 warps x 3 stages x 8 KiB = 96 KiB per CTA -> two CTAs per SM
+  static int env_w = -1;
+  if (env_w < 0) { const char* e = getenv("VCB_SKINNY_TMA_WARPS"); env_w = e ? atoi(e) : 0; }
+  if (env_w == 2 || env_w == 4 || env_w == 8) warps = env_w;
+  CUtensorMap tm;
+  VCB_TRY(make_tmap_w3d(&tm, p.W, p.K, p.N));
+  KernelScope scope(kCatSkinny, stream);
+  switch (nb) {
+    case 1: return launch_tma_w<1>(tm, p, grid, warps, stream);
+    case 2: return launch_tma_w<2>(tm, p, grid, warps, stream);
+    case 3: return launch_tma_w<3>(tm, p, grid, warps, stream);
+    default: return launch_tma_w<4>(tm, p, grid, warps, stream);
+  }
+}
+
+}  // namespace vcb
