@@ -1,0 +1,96 @@
+"""`load_pretrained_model` — mirror of vcoder_llava/model/builder.py:25-154 for the accelerated path.
+
+Same signature and the same 6-tuple `(tokenizer, model, image_processor, seg_image_processor, depth_image_processor,
+context_len)`; the model object is `vcoder_b200.model.VCoder{,DS}LlavaLlamaForCausalLM` (weights copied into
+libvcoder_b200.so) instead of an HF nn.Module.  Class dispatch by substring of `model_name` as in the reference
+(`builder.py:93-108`).  Quantised loading (`load_8bit` / `load_4bit`, bitsandbytes) is SURVEY §8 row f4 and raises.
+"""
+from __future__ import annotations
+
+import glob
+import json
+import os
+from typing import Dict
+
+import torch
+
+from . import synth
+from .model import build_model
+from .synth import ModelGeometry
+
+_VT = "model.vision_tower.vision_tower."
+
+
+def _read_state_dict(path: str) -> Dict[str, torch.Tensor]:
+    sd: Dict[str, torch.Tensor] = {}
+    st = sorted(glob.glob(os.path.join(path, "*.safetensors")))
+    if st:
+        from safetensors.torch import load_file
+        for f in st:
+            sd.update(load_file(f))
+        return sd
+    for f in sorted(glob.glob(os.path.join(path, "pytorch_model*.bin"))):
+        sd.update(torch.load(f, map_location="cpu"))
+    if not sd:
+        raise FileNotFoundError(f"no *.safetensors / pytorch_model*.bin under {path}")
+    return sd
+
+
+def geometry_from_configs(cfg: dict, vcfg: dict, variant: int) -> ModelGeometry:
+    """HF config.json keys the reference reads (vcoder_ds_llava_arch.py:34-49, CLIPVisionConfig, LlamaConfig)."""
+    return ModelGeometry(
+        name=cfg.get("_name_or_path", "checkpoint"), variant=variant,
+        vit_image_size=vcfg.get("image_size", 336), vit_patch=vcfg.get("patch_size", 14),
+        vit_hidden=vcfg.get("hidden_size", 1024), vit_heads=vcfg.get("num_attention_heads", 16),
+        vit_ffn=vcfg.get("intermediate_size", 4096), vit_layers=vcfg.get("num_hidden_layers", 24),
+        vit_select_layer=cfg.get("mm_vision_select_layer", -2), vit_ln_eps=vcfg.get("layer_norm_eps", 1e-5),
+        llm_hidden=cfg["hidden_size"], llm_layers=cfg["num_hidden_layers"], llm_heads=cfg["num_attention_heads"],
+        llm_ffn=cfg["intermediate_size"], llm_vocab=cfg["vocab_size"], llm_rms_eps=cfg.get("rms_norm_eps", 1e-5),
+        llm_rope_theta=cfg.get("rope_theta", 10000.0))
+
+
+def load_pretrained_model(model_path, model_base, model_name, load_8bit=False, load_4bit=False, device_map="auto",
+                          device="cuda", tokenizer=None, max_batch: int = 8):
+    if load_8bit or load_4bit:
+        raise NotImplementedError("bitsandbytes 8/4-bit loading is SURVEY §8 row f4 (next); fp16 only")
+    if model_base is not None:
+        raise NotImplementedError("LoRA / delta checkpoints: merge offline with the reference's scripts/merge_lora_weights.py")
+    name = model_name.lower()
+    if "vcoder_ds_llava" in name:
+        variant = synth.VARIANT_VCODER_DS
+    elif "vcoder_llava" in name:
+        variant = synth.VARIANT_VCODER
+    else:
+        raise ValueError(f"{model_name}: only vcoder_llava / vcoder_ds_llava models are on the accelerated path")
+    cfg = json.load(open(os.path.join(model_path, "config.json")))
+    tower_path = cfg["mm_vision_tower"]
+    vcfg_path = os.path.join(tower_path, "config.json")
+    vcfg = json.load(open(vcfg_path)) if os.path.exists(vcfg_path) else {}
+    vcfg = vcfg.get("vision_config", vcfg)
+    g = geometry_from_configs(cfg, vcfg, variant)
+
+    if tokenizer is None:
+        from transformers import AutoTokenizer
+        tokenizer = AutoTokenizer.from_pretrained(model_path, use_fast=False)  # builder.py:92
+
+    sd = _read_state_dict(model_path)
+    # the CLIP tower is delay-loaded from its own checkpoint by the reference (builder.py:138-143)
+    if not any(k.startswith(_VT) for k in sd):
+        tower_sd = _read_state_dict(tower_path)
+        for k, v in tower_sd.items():
+            if k.startswith("vision_model."):
+                sd[_VT + k] = v
+    image_processor = seg_image_processor = depth_image_processor = None
+    try:
+        from transformers import CLIPImageProcessor
+        image_processor = CLIPImageProcessor.from_pretrained(tower_path)
+        seg_image_processor = image_processor  # builder.py:146-151: same processor object for every modality
+        depth_image_processor = image_processor if variant == synth.VARIANT_VCODER_DS else None
+    except Exception:
+        pass
+
+    context_len = cfg.get("max_sequence_length", 2048)  # builder.py:133-136
+    dev_index = torch.device(device).index or 0
+    model = build_model(model_name, g, sd, max_batch=max_batch, max_seq_len=max(context_len, 2048), device=dev_index,
+                        image_processor=image_processor)
+    return tokenizer, model, image_processor, seg_image_processor, depth_image_processor, context_len

@@ -273,7 +273,7 @@ int attn_vit(const AttnPrefillParams& p, cudaStream_t stream) {
   static int use_tc5 = -1;
   if (use_tc5 < 0) {
     const char* e = getenv("VCB_VIT_ATTN");
-    use_tc5 = (e != nullptr && std::string(e) == "tc5") ? 1 : 0;  // default stays on the verified kernel until tc5 is green
+    use_tc5 = (e != nullptr && std::string(e) == "legacy") ? 0 : 1;  // tcgen05 kernel by default (parity-green, faster)
   }
   const bool packed = p.q_stride == p.kv_stride && p.k == p.q + p.n_heads * 64 && p.v == p.q + 2 * p.n_heads * 64;
   if (use_tc5 && packed && p.seq_len <= 640 && p.q_stride % 8 == 0) return attn_vit_tc5(p, stream);

@@ -2,17 +2,18 @@
 // Reference: CLIPVisionTower.forward -> transformers/models/clip/modeling_clip.py:261-345 (eager attention, no mask);
 // SURVEY K4 — the kernel the north star names (4,726,784 algorithmic bytes and 1.364 GFLOP per image-layer at S=577).
 //
-// One CTA = one (image, head, 128-query tile); TWO CTAs are resident per SM (<= 113 KiB smem, 256 TMEM columns each) so
-// that one CTA's exponentials (MUFU-bound) overlap the other's MMA / TMA latencies.
+// One CTA = one (image, head, 128-query tile); TWO CTAs are resident per SM (<= 113 KiB smem, 256 TMEM columns each).
 // TMA drops Q and a 2-deep ring of K and V tiles straight from the packed [tokens, 3*D] QKV buffer into 128B-swizzled
 // shared memory (one 2-D tensor map, three column offsets).
 //   warp 0 / lane 0 : TMA producer
-//   warp 1 / lane 0 : MMA issuer    S_j = Q K_j^T  (128x128x64, SS)                      -> TMEM S      (fp32)
-//                                    O_j = P_j V_j  (128x64x128, SS, V = MN-major B operand) -> TMEM O[j&1]
-//   warps 2..5      : softmax, one thread per query row: tcgen05.ld the score row, running max / sum in fp32,
-//                     P_j (fp16) written to swizzled smem as the next MMA's A operand, O_j pulled out of TMEM and
-//                     folded into fp32 registers with the online-softmax correction; final O / l stored as fp16.
-// Scores and probabilities never leave the SM.
+//   warp 1 / lane 0 : MMA issuer    S_j = Q K_j^T  (128x128x64, SS)                          -> TMEM S  (fp32)
+//                                    O  += P_j V_j  (128x64x128, SS, V = MN-major B operand)  -> TMEM O  (fp32)
+//   warps 2..9      : softmax, two threads per query row (64 key columns each).
+// The measured limiter of this kernel class is the TMEM read port (64 B/clk/SM) together with MUFU (16 exp/clk/SM), so
+// the data flow is built around reading every score exactly once: a thread pulls its 64 scores into registers (which
+// frees the S buffer for the next QK^T immediately), the two half-row maxima are exchanged through smem, and O stays in
+// TMEM across key blocks — it is only touched by the CUDA cores when the running max grows by more than 2^8 (lazy
+// rescale, as in FlashAttention-4), and once at the end for the 1/l normalisation.
 #include <cstdio>
 #include <cstdlib>
 
@@ -27,11 +28,13 @@ constexpr int kQ = 128;              // query rows per CTA
 constexpr int kKB = 128;             // keys per block
 constexpr int kDh = 64;
 constexpr int kTile = kQ * kDh * 2;  // 16 KiB: one [128 x 64] fp16 tile (Q, K_j or V_j); also one 64-key half of P
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;        // TMA warp + MMA warp + 8 softmax warps
+constexpr int kSoftThreads = 256;
 // smem: Q | K[2] | V[2] | P (2 x 16 KiB) | barriers      (dynamic smem base must be 1 KiB aligned: checked at run time)
-constexpr int kSmemBytes = kTile * (1 + 2 + 2 + 2) + 256;
-constexpr uint32_t kColS = 0, kColO = 128;  // TMEM columns: S at 0, O[2] at 128/192
+constexpr int kSmemBytes = kTile * (1 + 2 + 2 + 2) + 256;  // 114,944 B: two CTAs per SM
+constexpr uint32_t kColS = 0, kColO = 128;                 // TMEM columns: S at 0, O at 128
 constexpr uint32_t kTmemCols = 256;
+constexpr float kRescaleLog2 = 8.0f;  // P stays below 2^8: exact enough in fp16, far from overflow
 
 struct VitTc5Params {
   __half* out;
@@ -43,8 +46,8 @@ struct VitTc5Params {
 };
 
 enum {
-  kBarQ = 0, kBarKFull = 1, kBarKEmpty = 3, kBarVFull = 5, kBarVEmpty = 7, kBarS = 9, kBarP = 10, kBarO = 11,
-  kBarOC = 13, kNumBars = 15
+  kBarQ = 0, kBarKFull = 1, kBarKEmpty = 3, kBarVFull = 5, kBarVEmpty = 7, kBarS = 9, kBarSFree = 10, kBarP = 11,
+  kBarO = 12, kNumBars = 13
 };
 
 __global__ void __launch_bounds__(kThreads, 2)
@@ -65,7 +68,7 @@ attn_vit_tc5_kernel(const __grid_constant__ CUtensorMap tm, VitTc5Params p) {
   const int row_base = b * S;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kNumBars; ++i) mbar_init(bar(i), (i == kBarP || i == kBarOC || i == kBarOC + 1) ? 4 : 1);
+    for (int i = 0; i < kNumBars; ++i) mbar_init(bar(i), (i == kBarP || i == kBarSFree) ? 8 : 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -117,135 +120,164 @@ attn_vit_tc5_kernel(const __grid_constant__ CUtensorMap tm, VitTc5Params p) {
           const uint32_t vaddr = sV + slot * kTile + s * 2048;  // 16 keys = 16 rows of 128 B
           const uint64_t vdesc = (static_cast<uint64_t>(p.v_desc_hi) << 32) | (static_cast<uint64_t>(p.v_lbo) << 16) |
                                  static_cast<uint64_t>((vaddr & 0x3FFFF) >> 4);
-          umma_f16(tmem + kColO + slot * kDh, pdesc, vdesc, idesc_o, s != 0 ? 1u : 0u);
+          umma_f16(tmem + kColO, pdesc, vdesc, idesc_o, (j > 0 || s > 0) ? 1u : 0u);
         }
-        umma_commit(bar(kBarO + slot));
+        umma_commit(bar(kBarO));
         umma_commit(bar(kBarVEmpty + slot));
       };
       mbar_wait(bar(kBarQ), 0);
       issue_s(0);
       for (int j = 0; j < nb; ++j) {
-        mbar_wait(bar(kBarP), j & 1);  // P_j is in smem and S_j has been read out of TMEM
+        if (j + 1 < nb) {
+          mbar_wait(bar(kBarSFree), j & 1);  // the softmax warps hold S_j in registers: S may be overwritten
+          tc_fence_after();
+          issue_s(j + 1);
+        }
+        mbar_wait(bar(kBarP), j & 1);  // P_j is in smem (and O has been rescaled if that was needed)
         mbar_wait(bar(kBarVFull + (j & 1)), (j >> 1) & 1);
-        if (j >= 2) mbar_wait(bar(kBarOC + (j & 1)), ((j >> 1) - 1) & 1);  // O_{j-2} has been read out of TMEM
         tc_fence_after();
         issue_pv(j);
-        if (j + 1 < nb) issue_s(j + 1);
       }
     }
   } else {
-    // ------------------------------------------------------------ softmax warps: thread = query row
-    const int q = warp & 3;        // TMEM lane quadrant of this warp
-    const int r = q * 32 + lane;   // row within the tile
+    // ------------------------------------------------------------ softmax warps: two threads per query row
+    const int q = warp & 3;            // TMEM lane quadrant of this warp (hardware rule: warp id % 4)
+    const int half = (warp - 2) >> 2;  // which 64 key columns of each block / which 32 columns of O this thread owns
+    const int r = q * 32 + lane;       // row within the tile
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const float sc = p.scale_log2;
-    float o[kDh];
-#pragma unroll
-    for (int i = 0; i < kDh; ++i) o[i] = 0.f;
-    float M = -INFINITY, L = 0.f, corr_prev = 0.f;
+    const uint32_t s_addr = tmem + lane_off + kColS + half * 64;
+    const uint32_t o_addr = tmem + lane_off + kColO + half * 32;
+    uint8_t* my_row = smem + (sP - base) + half * kTile + r * 128;            // this thread's 64 keys of P
+    float* my_slot = reinterpret_cast<float*>(my_row);                         // partner -> me
+    float* partner_slot = reinterpret_cast<float*>(smem + (sP - base) + (half ^ 1) * kTile + r * 128);  // me -> partner
+    float Mref = -INFINITY, L = 0.f;
 
-    auto fold_o = [&](int j, float corr) {  // o = o * corr + O_j
-      mbar_wait(bar(kBarO + (j & 1)), (j >> 1) & 1);
-      tc_fence_after();
-      uint32_t v0[32], v1[32];
-      tmem_ld_32x32(tmem + lane_off + kColO + (j & 1) * kDh, v0);
-      tmem_ld_32x32(tmem + lane_off + kColO + (j & 1) * kDh + 32, v1);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        o[i] = fmaf(o[i], corr, __uint_as_float(v0[i]));
-        o[32 + i] = fmaf(o[32 + i], corr, __uint_as_float(v1[i]));
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(kBarOC + (j & 1)));
-    };
-
-    const uint32_t s_addr = tmem + lane_off + kColS;
     for (int j = 0; j < nb; ++j) {
-      const int nkeys = min(kKB, S - j * kKB);
-      const int nchunks = (nkeys + 31) / 32;
+      const int nk = min(kKB, S - j * kKB) - half * 64;  // valid keys among this thread's 64 columns (may be <= 0)
       mbar_wait(bar(kBarS), j & 1);
       tc_fence_after();
-      // pass A: block max.  Only the last chunk of the last key block is partial: full chunks take the mask-free path.
-      float mx0 = M, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-      for (int c = 0; c < nchunks; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(s_addr + c * 32, v);
-        tmem_ld_wait();
-        const int valid = nkeys - c * 32;
-        if (valid >= 32) {
+      uint32_t v[2][32];
+      tmem_ld_32x32(s_addr, v[0]);
+      tmem_ld_32x32(s_addr + 32, v[1]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(kBarSFree));  // S_{j+1} may start while we exponentiate S_j
+
+      // local max over this thread's valid columns
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+      if (nk >= 64) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
-            mx0 = fmaxf(mx0, __uint_as_float(v[i]));
-            mx1 = fmaxf(mx1, __uint_as_float(v[i + 1]));
-            mx2 = fmaxf(mx2, __uint_as_float(v[i + 2]));
-            mx3 = fmaxf(mx3, __uint_as_float(v[i + 3]));
+            mx0 = fmaxf(mx0, __uint_as_float(v[c][i]));
+            mx1 = fmaxf(mx1, __uint_as_float(v[c][i + 1]));
+            mx2 = fmaxf(mx2, __uint_as_float(v[c][i + 2]));
+            mx3 = fmaxf(mx3, __uint_as_float(v[c][i + 3]));
           }
-        } else {
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (i < valid) mx0 = fmaxf(mx0, __uint_as_float(v[i]));
+            if (c * 32 + i < nk) mx0 = fmaxf(mx0, __uint_as_float(v[c][i]));
         }
       }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      const float corr = fast_exp2((M - mx) * sc);  // M = -inf on the first block -> 0
-      const float msc = mx * sc;
-      M = mx;
-      // the previous block's PV result (also frees the P buffer for this block's probabilities)
-      if (j > 0) fold_o(j - 1, corr_prev);
-      corr_prev = corr;
-      // pass B: probabilities -> fp16 -> swizzled smem (A operand of the PV MMA), row sum
-      float l = 0.f;
-      for (int c = 0; c < nchunks; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(s_addr + c * 32, v);
+      const float mloc = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+
+      // P_{j-1} V_{j-1} must be complete before the P tile is reused (exchange slot, then P_j) or O is rescaled
+      if (j > 0) {
+        mbar_wait(bar(kBarO), (j - 1) & 1);
+        tc_fence_after();
+      }
+      *partner_slot = mloc;  // lives in the partner's P row: the partner reads it, then overwrites it with its P_j
+      asm volatile("bar.sync 1, %0;" ::"n"(kSoftThreads) : "memory");
+      const float mblk = fmaxf(mloc, *my_slot);
+
+      // lazy rescale: keep the old reference max unless the row max grew by more than 2^kRescaleLog2
+      float f = 1.f;
+      if (j == 0) {
+        Mref = mblk;
+      } else if ((mblk - Mref) * sc > kRescaleLog2) {
+        f = fast_exp2((Mref - mblk) * sc);
+        Mref = mblk;
+        L *= f;
+      }
+      if (j > 0 && __any_sync(0xffffffffu, f != 1.f)) {  // warp-uniform: tcgen05.ld/st are warp-collective
+        uint32_t ov[32];
+        tmem_ld_32x32(o_addr, ov);
         tmem_ld_wait();
-        uint32_t pk[16];
-        const int valid = nkeys - c * 32;
-        if (valid >= 32) {
-          float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = fast_exp2(fmaf(__uint_as_float(v[i]), sc, -msc));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), sc, -msc));
-            l0 += p0;
-            l1 += p1;
-            pk[i >> 1] = pack_half2(p0, p1);
+        for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * f);
+        tmem_st_32x32(o_addr, ov);
+        tmem_st_wait();
+      }
+      const float msc = Mref * sc;
+
+      // probabilities -> fp16 -> swizzled smem (A operand of the PV MMA), partial row sum
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        if (c * 32 < nk) {
+          uint32_t pk[16];
+          if (nk >= (c + 1) * 32) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float p0 = fast_exp2(fmaf(__uint_as_float(v[c][i]), sc, -msc));
+              const float p1 = fast_exp2(fmaf(__uint_as_float(v[c][i + 1]), sc, -msc));
+              l0 += p0;
+              l1 += p1;
+              pk[i >> 1] = pack_half2(p0, p1);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float p0 = (c * 32 + i < nk) ? fast_exp2(fmaf(__uint_as_float(v[c][i]), sc, -msc)) : 0.f;
+              const float p1 = (c * 32 + i + 1 < nk) ? fast_exp2(fmaf(__uint_as_float(v[c][i + 1]), sc, -msc)) : 0.f;
+              l0 += p0;
+              l1 += p1;
+              pk[i >> 1] = pack_half2(p0, p1);
+            }
           }
-          l += l0 + l1;
-        } else {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = (i < valid) ? fast_exp2(fmaf(__uint_as_float(v[i]), sc, -msc)) : 0.f;
-            const float p1 = (i + 1 < valid) ? fast_exp2(fmaf(__uint_as_float(v[i + 1]), sc, -msc)) : 0.f;
-            l += p0 + p1;
-            pk[i >> 1] = pack_half2(p0, p1);
+          for (int w = 0; w < 4; ++w) {
+            const int chunk = (c * 4 + w) ^ (r & 7);
+            *reinterpret_cast<uint4*>(my_row + (chunk << 4)) = make_uint4(pk[4 * w], pk[4 * w + 1], pk[4 * w + 2], pk[4 * w + 3]);
           }
-        }
-        // keys [c*32, c*32+32) of row r: 64-key half (c>>1), 16-byte chunks (c&1)*4 .. +3 of the 128-byte row
-        uint8_t* prow = smem + (sP - base) + (c >> 1) * kTile + r * 128;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          const int chunk = ((c & 1) * 4 + w) ^ (r & 7);
-          *reinterpret_cast<uint4*>(prow + (chunk << 4)) = make_uint4(pk[4 * w], pk[4 * w + 1], pk[4 * w + 2], pk[4 * w + 3]);
         }
       }
-      L = L * corr + l;
+      L += l0 + l1;
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(kBarP));
     }
-    fold_o(nb - 1, corr_prev);
+
+    // ---- epilogue: O (TMEM) / l  -> fp16
+    mbar_wait(bar(kBarO), (nb - 1) & 1);
+    tc_fence_after();
+    uint32_t ov[32];
+    tmem_ld_32x32(o_addr, ov);
+    tmem_ld_wait();
+    // total row sum = the two halves' partial sums (both relative to the same reference max).  The P tile is free now.
+    float* xb = reinterpret_cast<float*>(smem + (sP - base));
+    xb[half * kQ + r] = L;
+    asm volatile("bar.sync 1, %0;" ::"n"(kSoftThreads) : "memory");
+    L += xb[(half ^ 1) * kQ + r];
     const int row = q0 + r;
     if (row < S) {
       const float inv = 1.f / L;
-      uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<long>(row_base + row) * p.out_stride + h * kDh);
+      uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<long>(row_base + row) * p.out_stride + h * kDh + half * 32);
 #pragma unroll
-      for (int w = 0; w < 8; ++w) {
-        dst[w] = make_uint4(pack_half2(o[8 * w] * inv, o[8 * w + 1] * inv), pack_half2(o[8 * w + 2] * inv, o[8 * w + 3] * inv),
-                            pack_half2(o[8 * w + 4] * inv, o[8 * w + 5] * inv), pack_half2(o[8 * w + 6] * inv, o[8 * w + 7] * inv));
+      for (int w = 0; w < 4; ++w) {
+        dst[w] = make_uint4(
+            pack_half2(__uint_as_float(ov[8 * w]) * inv, __uint_as_float(ov[8 * w + 1]) * inv),
+            pack_half2(__uint_as_float(ov[8 * w + 2]) * inv, __uint_as_float(ov[8 * w + 3]) * inv),
+            pack_half2(__uint_as_float(ov[8 * w + 4]) * inv, __uint_as_float(ov[8 * w + 5]) * inv),
+            pack_half2(__uint_as_float(ov[8 * w + 6]) * inv, __uint_as_float(ov[8 * w + 7]) * inv));
       }
     }
   }

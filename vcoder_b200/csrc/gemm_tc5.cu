@@ -307,12 +307,12 @@ int make_tmap_2d_f16(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t r
 }
 
 // W [N, K] row-major viewed as [K/64][N][64] for the TMA-fed skinny GEMM: box = 4 k-blocks x 16 rows x 64 k (8 KiB)
-int make_tmap_w3d(CUtensorMap* m, const void* ptr, uint64_t K, uint64_t N) {
+int make_tmap_w3d(CUtensorMap* m, const void* ptr, uint64_t K, uint64_t N, uint32_t box_kblocks) {
   EncodeTiledFn fn = get_encode_fn();
   VCB_CHECK(fn != nullptr, kErrCuda, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[3] = {64, N, K / 64};
   cuuint64_t strides[2] = {K * 2, 128};
-  cuuint32_t box[3] = {64, 16, 4};
+  cuuint32_t box[3] = {64, 16, box_kblocks};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -245,7 +245,7 @@ int skinny_gemm_tma(const SkinnyParams& p, cudaStream_t stream);
 int skinny_gemm(const SkinnyParams& p, cudaStream_t stream) {
   {
     static int impl = -1;  // 0 = LDG kernel (this file), 1 = TMA-fed kernel (skinny_tma.cu)
-    if (impl < 0) { const char* e = getenv("VCB_SKINNY_IMPL"); impl = (e && std::string(e) == "tma") ? 1 : 0; }
+    if (impl < 0) { const char* e = getenv("VCB_SKINNY_IMPL"); impl = (e && std::string(e) == "ldg") ? 0 : 1; }  // default: TMA-fed (measured faster)
     if (impl == 1 && p.K % 64 == 0 && p.norm_w == nullptr) return skinny_gemm_tma(p, stream);
   }
   VCB_CHECK(p.B >= 1 && p.B <= 32, kErrInvalid, "skinny_gemm: batch must be in [1, 32]");
@@ -255,7 +255,7 @@ int skinny_gemm(const SkinnyParams& p, cudaStream_t stream) {
   const int grid = p.N / 16;
   const int nb = (p.B + 7) / 8;
   // aim for >= ~32 resident warps per SM
-  int warps = grid <= 512 ? 16 : (grid <= 1024 ? 8 : 4);
+  int warps = grid <= 512 ? 16 : 8;  // measured: 8 warps + contiguous k-ranges (mode 1) is the best LDG variant
   SkinnyParams pp = p;
   {
     static int env_mode = -1;

@@ -15,9 +15,6 @@ namespace vcb {
 namespace {
 
 constexpr int kKBlk = 64;               // k elements per 128-byte swizzled row
-constexpr int kGroup = 4;               // k-blocks per TMA box
-constexpr int kStageBytes = kGroup * 16 * kKBlk * 2;  // 8 KiB
-constexpr int kDepth = 3;               // stages in flight per warp
 
 __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                           uint32_t b0, uint32_t b1) {
@@ -34,9 +31,10 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + fast_exp2(-1.4426950408889634f * x)); }
 
 // W viewed as a 3-D tensor [K/64][N][64]: dim0 = k within a 64-block, dim1 = row, dim2 = k-block
-template <int NB, int WARPS>
+template <int NB, int WARPS, int kDepth, int kGroup>
 __global__ void __launch_bounds__(WARPS * 32)
 skinny_tma_kernel(const __grid_constant__ CUtensorMap tmW, SkinnyParams p) {
+  constexpr int kStageBytes = kGroup * 16 * kKBlk * 2;  // kGroup k-blocks x 16 rows x 128 B
   extern __shared__ __align__(1024) uint8_t smem[];  // [WARPS][kDepth] stages | red | barriers (no static smem: base stays 1 KiB aligned)
   typedef float RedT[16][8 * NB + 1];
   RedT* red = reinterpret_cast<RedT*>(smem + WARPS * kDepth * kStageBytes);
@@ -154,27 +152,39 @@ skinny_tma_kernel(const __grid_constant__ CUtensorMap tmW, SkinnyParams p) {
   }
 }
 
-template <int NB, int WARPS>
+template <int NB, int WARPS, int kDepth, int kGroup>
 int launch_tma(const CUtensorMap& tm, const SkinnyParams& p, int grid, cudaStream_t stream) {
+  constexpr int kStageBytes = kGroup * 16 * kKBlk * 2;
   constexpr int smem = WARPS * kDepth * kStageBytes + WARPS * 16 * (8 * NB + 1) * 4 + 8 + WARPS * kDepth * 8 + 16;
+  static_assert(smem <= 227 * 1024, "skinny_tma: ring does not fit in shared memory");
   static bool attr = false;
   if (!attr) {
-    VCB_CUDA(cudaFuncSetAttribute(skinny_tma_kernel<NB, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    VCB_CUDA(cudaFuncSetAttribute(skinny_tma_kernel<NB, WARPS, kDepth, kGroup>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr = true;
   }
-  VCB_CUDA(launch_pdl(skinny_tma_kernel<NB, WARPS>, dim3(grid), dim3(WARPS * 32), smem, stream, tm, p));
+  VCB_CUDA(launch_pdl(skinny_tma_kernel<NB, WARPS, kDepth, kGroup>, dim3(grid), dim3(WARPS * 32), smem, stream, tm, p));
   return kOk;
 }
 template <int NB>
-int launch_tma_w(const CUtensorMap& tm, const SkinnyParams& p, int grid, int warps, cudaStream_t stream) {
-  if (warps >= 8) return launch_tma<NB, 8>(tm, p, grid, stream);
-  if (warps >= 4) return launch_tma<NB, 4>(tm, p, grid, stream);
-  return launch_tma<NB, 2>(tm, p, grid, stream);
+int launch_tma_w(const CUtensorMap& tm, const SkinnyParams& p, int grid, int warps, int depth, int group,
+                 cudaStream_t stream) {
+  if (group == 2) {
+    if (depth <= 2) return launch_tma<NB, 4, 2, 2>(tm, p, grid, stream);
+    if (depth == 3) return launch_tma<NB, 4, 3, 2>(tm, p, grid, stream);
+    return launch_tma<NB, 4, 4, 2>(tm, p, grid, stream);
+  }
+  if (warps >= 8) return launch_tma<NB, 8, 2, 4>(tm, p, grid, stream);
+  if (warps >= 4) {
+    if (depth <= 2) return launch_tma<NB, 4, 2, 4>(tm, p, grid, stream);
+    return launch_tma<NB, 4, 3, 4>(tm, p, grid, stream);
+  }
+  if (depth <= 2) return launch_tma<NB, 2, 2, 4>(tm, p, grid, stream);
+  return launch_tma<NB, 2, 3, 4>(tm, p, grid, stream);
 }
 
 }  // namespace
 
-int make_tmap_w3d(CUtensorMap* m, const void* ptr, uint64_t K, uint64_t N);
+int make_tmap_w3d(CUtensorMap* m, const void* ptr, uint64_t K, uint64_t N, uint32_t box_kblocks);
 
 int skinny_gemm_tma(const SkinnyParams& p, cudaStream_t stream) {
   VCB_CHECK(p.B >= 1 && p.B <= 32, kErrInvalid, "skinny_gemm: batch must be in [1, 32]");
@@ -183,17 +193,22 @@ int skinny_gemm_tma(const SkinnyParams& p, cudaStream_t stream) {
   const int grid = p.N / 16;
   const int nb = (p.B + 7) / 8;
   int warps = 4;  // 4 warps x 3 stages x 8 KiB = 96 KiB per CTA -> two CTAs per SM
-  static int env_w = -1;
+  int depth = 2, group = 4;  // measured best on B200: 4 warps x 2 stages x 8 KiB -> three CTAs per SM
+  static int env_w = -1, env_d = -1, env_g = -1;
+  if (env_g < 0) { const char* e = getenv("VCB_SKINNY_TMA_GROUP"); env_g = e ? atoi(e) : 0; }
+  if (env_g == 2 || env_g == 4) group = env_g;
   if (env_w < 0) { const char* e = getenv("VCB_SKINNY_TMA_WARPS"); env_w = e ? atoi(e) : 0; }
+  if (env_d < 0) { const char* e = getenv("VCB_SKINNY_TMA_DEPTH"); env_d = e ? atoi(e) : 0; }
   if (env_w == 2 || env_w == 4 || env_w == 8) warps = env_w;
+  if (env_d > 0) depth = env_d;
   CUtensorMap tm;
-  VCB_TRY(make_tmap_w3d(&tm, p.W, p.K, p.N));
+  VCB_TRY(make_tmap_w3d(&tm, p.W, p.K, p.N, group));
   KernelScope scope(kCatSkinny, stream);
   switch (nb) {
-    case 1: return launch_tma_w<1>(tm, p, grid, warps, stream);
-    case 2: return launch_tma_w<2>(tm, p, grid, warps, stream);
-    case 3: return launch_tma_w<3>(tm, p, grid, warps, stream);
-    default: return launch_tma_w<4>(tm, p, grid, warps, stream);
+    case 1: return launch_tma_w<1>(tm, p, grid, warps, depth, group, stream);
+    case 2: return launch_tma_w<2>(tm, p, grid, warps, depth, group, stream);
+    case 3: return launch_tma_w<3>(tm, p, grid, warps, depth, group, stream);
+    default: return launch_tma_w<4>(tm, p, grid, warps, depth, group, stream);
   }
 }
 
