@@ -20,12 +20,11 @@ if which in ("all", "skinny"):
     B = 8
     for (N, K, sw) in [(12288, 4096, 0), (4096, 4096, 0), (22016, 4096, 1), (4096, 11008, 0), (32000, 4096, 0)]:
         X = (torch.randn(B, K, device=dev) * 0.5).half()
-        W = (torch.randn(N, K, device=dev) * 0.03).half()
+        Ws = [(torch.randn(N, K, device=dev) * 0.03).half() for _ in range(3)]
         No = N // 2 if sw else N
         Y = torch.empty(B, No, device=dev, dtype=torch.float16)
-        for _ in range(3):
-            flush.zero_()
-            lib.vcb_op_skinny_gemm_f16(_lib.ptr(X), K, _lib.ptr(W), B, N, K, None, N, sw, _lib.ptr(Y), No, st)
+        for i in range(3):
+            lib.vcb_op_skinny_gemm_f16(_lib.ptr(X), K, _lib.ptr(Ws[i]), B, N, K, None, N, sw, _lib.ptr(Y), No, st)
         torch.cuda.synchronize()
 if which in ("all", "attn"):
     Bi, S, heads = 24, 577, 16

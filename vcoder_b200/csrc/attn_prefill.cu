@@ -270,13 +270,15 @@ int attn_vit_legacy(const AttnPrefillParams& p, cudaStream_t stream) {
 }
 
 int attn_vit(const AttnPrefillParams& p, cudaStream_t stream) {
-  static int use_tc5 = -1;
+  static int use_tc5 = -1;  // 0 legacy mma.sync, 1 tcgen05 (one tile per CTA, two CTAs per SM), 2 tcgen05 pair schedule
   if (use_tc5 < 0) {
     const char* e = getenv("VCB_VIT_ATTN");
-    use_tc5 = (e != nullptr && std::string(e) == "legacy") ? 0 : 1;  // tcgen05 kernel by default (parity-green, faster)
+    const std::string v = e ? e : "";
+    use_tc5 = v == "legacy" ? 0 : (v == "pair" ? 2 : 1);
   }
   const bool packed = p.q_stride == p.kv_stride && p.k == p.q + p.n_heads * 64 && p.v == p.q + 2 * p.n_heads * 64;
-  if (use_tc5 && packed && p.seq_len <= 640 && p.q_stride % 8 == 0) return attn_vit_tc5(p, stream);
+  if (use_tc5 == 2 && packed && p.q_stride % 8 == 0) return attn_vit_pair(p, stream);
+  if (use_tc5 && packed && p.q_stride % 8 == 0) return attn_vit_tc5(p, stream);
   return attn_vit_legacy(p, stream);
 }
 

@@ -31,7 +31,8 @@ constexpr int kTile = kQ * kDh * 2;  // 16 KiB: one [128 x 64] fp16 tile (Q, K_j
 constexpr int kThreads = 320;        // TMA warp + MMA warp + 8 softmax warps
 constexpr int kSoftThreads = 256;
 // smem: Q | K[2] | V[2] | P (2 x 16 KiB) | barriers      (dynamic smem base must be 1 KiB aligned: checked at run time)
-constexpr int kSmemBytes = kTile * (1 + 2 + 2 + 2) + 256;  // 114,944 B: two CTAs per SM
+constexpr int kSmemBytes = kTile * (1 + 2 + 2 + 2) + 768;  // 115,456 B: two CTAs per SM (limit 115,712)
+constexpr int kOffXchg = 128;                              // inside the 768-byte tail: [barriers | tmem slot | fp16 row maxima]
 constexpr uint32_t kColS = 0, kColO = 128;                 // TMEM columns: S at 0, O at 128
 constexpr uint32_t kTmemCols = 256;
 constexpr float kRescaleLog2 = 8.0f;  // P stays below 2^8: exact enough in fp16, far from overflow
@@ -43,6 +44,7 @@ struct VitTc5Params {
   float scale_log2;    // scale * log2(e)
   uint32_t v_desc_hi;  // upper 32 bits of the V (MN-major) smem descriptor: SBO / version / layout
   uint32_t v_lbo;      // LBO field (>>4) of the V descriptor
+  long long* dbg;      // optional clock64 trace of CTA (0,0,0) (bring-up / profiling only)
 };
 
 enum {
@@ -111,16 +113,25 @@ attn_vit_tc5_kernel(const __grid_constant__ CUtensorMap tm, VitTc5Params p) {
         umma_commit(bar(kBarS));
         umma_commit(bar(kBarKEmpty + slot));
       };
+      // descriptors precomputed once: the issuing thread shares its SM sub-partition with two softmax warps, so every
+      // instruction between "P is ready" and the tcgen05.mma issue is exposed latency
+      const uint64_t pdesc0 = make_sw128_kmajor_desc(sP), pdesc1 = make_sw128_kmajor_desc(sP + kTile);
+      const uint64_t vdesc_hi = (static_cast<uint64_t>(p.v_desc_hi) << 32) | (static_cast<uint64_t>(p.v_lbo) << 16);
+      const uint64_t vdesc_s0 = vdesc_hi | static_cast<uint64_t>((sV & 0x3FFFF) >> 4);
+      const uint64_t vdesc_s1 = vdesc_hi | static_cast<uint64_t>(((sV + kTile) & 0x3FFFF) >> 4);
       auto issue_pv = [&](int j) {
         const int slot = j & 1;
         const int nkeys = min(kKB, S - j * kKB);
-        const int ksteps = (nkeys + 15) / 16;
-        for (int s = 0; s < ksteps; ++s) {
-          const uint64_t pdesc = make_sw128_kmajor_desc(sP + (s >> 2) * kTile) + 2 * (s & 3);
-          const uint32_t vaddr = sV + slot * kTile + s * 2048;  // 16 keys = 16 rows of 128 B
-          const uint64_t vdesc = (static_cast<uint64_t>(p.v_desc_hi) << 32) | (static_cast<uint64_t>(p.v_lbo) << 16) |
-                                 static_cast<uint64_t>((vaddr & 0x3FFFF) >> 4);
-          umma_f16(tmem + kColO, pdesc, vdesc, idesc_o, (j > 0 || s > 0) ? 1u : 0u);
+        const uint64_t vd = slot ? vdesc_s1 : vdesc_s0;
+        const uint32_t acc0 = j > 0 ? 1u : 0u;
+        if (nkeys == kKB) {
+#pragma unroll
+          for (int s = 0; s < 8; ++s)  // 16 keys per step: +32 B along P's k, +2048 B (16 rows) along V
+            umma_f16(tmem + kColO, (s < 4 ? pdesc0 : pdesc1) + 2 * (s & 3), vd + 128 * s, idesc_o, s == 0 ? acc0 : 1u);
+        } else {
+          const int ksteps = (nkeys + 15) / 16;
+          for (int s = 0; s < ksteps; ++s)
+            umma_f16(tmem + kColO, (s < 4 ? pdesc0 : pdesc1) + 2 * (s & 3), vd + 128 * s, idesc_o, s == 0 ? acc0 : 1u);
         }
         umma_commit(bar(kBarO));
         umma_commit(bar(kBarVEmpty + slot));
@@ -134,9 +145,11 @@ attn_vit_tc5_kernel(const __grid_constant__ CUtensorMap tm, VitTc5Params p) {
           issue_s(j + 1);
         }
         mbar_wait(bar(kBarP), j & 1);  // P_j is in smem (and O has been rescaled if that was needed)
+        if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.dbg[j * 8 + 6] = clock64();
         mbar_wait(bar(kBarVFull + (j & 1)), (j >> 1) & 1);
         tc_fence_after();
         issue_pv(j);
+        if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.dbg[j * 8 + 7] = clock64();
       }
     }
   } else {
@@ -149,14 +162,17 @@ attn_vit_tc5_kernel(const __grid_constant__ CUtensorMap tm, VitTc5Params p) {
     const uint32_t s_addr = tmem + lane_off + kColS + half * 64;
     const uint32_t o_addr = tmem + lane_off + kColO + half * 32;
     uint8_t* my_row = smem + (sP - base) + half * kTile + r * 128;            // this thread's 64 keys of P
-    float* my_slot = reinterpret_cast<float*>(my_row);                         // partner -> me
-    float* partner_slot = reinterpret_cast<float*>(smem + (sP - base) + (half ^ 1) * kTile + r * 128);  // me -> partner
+    __half* xchg = reinterpret_cast<__half*>(smem + (bars - base) + kOffXchg);     // [2 halves][128 rows] fp16 row maxima
     float Mref = -INFINITY, L = 0.f;
 
+    const bool trace = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 2 && lane == 0;
+#define VCB_STAMP(slot) do { if (trace) p.dbg[(j) * 8 + (slot)] = clock64(); } while (0)
     for (int j = 0; j < nb; ++j) {
       const int nk = min(kKB, S - j * kKB) - half * 64;  // valid keys among this thread's 64 columns (may be <= 0)
+      VCB_STAMP(0);
       mbar_wait(bar(kBarS), j & 1);
       tc_fence_after();
+      VCB_STAMP(1);
       uint32_t v[2][32];
       tmem_ld_32x32(s_addr, v[0]);
       tmem_ld_32x32(s_addr + 32, v[1]);
@@ -164,6 +180,7 @@ attn_vit_tc5_kernel(const __grid_constant__ CUtensorMap tm, VitTc5Params p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(kBarSFree));  // S_{j+1} may start while we exponentiate S_j
+      VCB_STAMP(2);
 
       // local max over this thread's valid columns
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
@@ -188,14 +205,15 @@ attn_vit_tc5_kernel(const __grid_constant__ CUtensorMap tm, VitTc5Params p) {
       }
       const float mloc = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
 
-      // P_{j-1} V_{j-1} must be complete before the P tile is reused (exchange slot, then P_j) or O is rescaled
-      if (j > 0) {
-        mbar_wait(bar(kBarO), (j - 1) & 1);
-        tc_fence_after();
-      }
-      *partner_slot = mloc;  // lives in the partner's P row: the partner reads it, then overwrites it with its P_j
+      // exchange the half-row maxima through dedicated fp16 slots (both threads then use the same reference max).
+      // The slot may be overwritten once the partner has read the previous block's value, i.e. after every warp has
+      // arrived on bar_p of block j-1.
+      if (j > 0) mbar_wait(bar(kBarP), (j - 1) & 1);
+      const __half mh = __float2half_rn(fminf(fmaxf(mloc, -60000.f), 60000.f));
+      xchg[half * kQ + r] = mh;
       asm volatile("bar.sync 1, %0;" ::"n"(kSoftThreads) : "memory");
-      const float mblk = fmaxf(mloc, *my_slot);
+      const float mblk = fmaxf(__half2float(mh), __half2float(xchg[(half ^ 1) * kQ + r]));
+      VCB_STAMP(3);
 
       // lazy rescale: keep the old reference max unless the row max grew by more than 2^kRescaleLog2
       float f = 1.f;
@@ -206,7 +224,11 @@ attn_vit_tc5_kernel(const __grid_constant__ CUtensorMap tm, VitTc5Params p) {
         Mref = mblk;
         L *= f;
       }
+      bool waited_o = false;
       if (j > 0 && __any_sync(0xffffffffu, f != 1.f)) {  // warp-uniform: tcgen05.ld/st are warp-collective
+        mbar_wait(bar(kBarO), (j - 1) & 1);  // P_{j-1} V_{j-1} has landed in O
+        tc_fence_after();
+        waited_o = true;
         uint32_t ov[32];
         tmem_ld_32x32(o_addr, ov);
         tmem_ld_wait();
@@ -216,36 +238,46 @@ attn_vit_tc5_kernel(const __grid_constant__ CUtensorMap tm, VitTc5Params p) {
         tmem_st_wait();
       }
       const float msc = Mref * sc;
+      VCB_STAMP(4);
 
-      // probabilities -> fp16 -> swizzled smem (A operand of the PV MMA), partial row sum
+      // probabilities (fp16 pairs) into registers first: the MUFU work overlaps the PV MMA of the previous block
+      uint32_t pk[2][16];
       float l0 = 0.f, l1 = 0.f;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        if (c * 32 < nk) {
-          uint32_t pk[16];
-          if (nk >= (c + 1) * 32) {
+        if (nk >= (c + 1) * 32) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float p0 = fast_exp2(fmaf(__uint_as_float(v[c][i]), sc, -msc));
-              const float p1 = fast_exp2(fmaf(__uint_as_float(v[c][i + 1]), sc, -msc));
-              l0 += p0;
-              l1 += p1;
-              pk[i >> 1] = pack_half2(p0, p1);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float p0 = (c * 32 + i < nk) ? fast_exp2(fmaf(__uint_as_float(v[c][i]), sc, -msc)) : 0.f;
-              const float p1 = (c * 32 + i + 1 < nk) ? fast_exp2(fmaf(__uint_as_float(v[c][i + 1]), sc, -msc)) : 0.f;
-              l0 += p0;
-              l1 += p1;
-              pk[i >> 1] = pack_half2(p0, p1);
-            }
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(v[c][i]), sc, -msc));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(v[c][i + 1]), sc, -msc));
+            l0 += p0;
+            l1 += p1;
+            pk[c][i >> 1] = pack_half2(p0, p1);
           }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = (c * 32 + i < nk) ? fast_exp2(fmaf(__uint_as_float(v[c][i]), sc, -msc)) : 0.f;
+            const float p1 = (c * 32 + i + 1 < nk) ? fast_exp2(fmaf(__uint_as_float(v[c][i + 1]), sc, -msc)) : 0.f;
+            l0 += p0;
+            l1 += p1;
+            pk[c][i >> 1] = pack_half2(p0, p1);
+          }
+        }
+      }
+      // the P tile is free once P_{j-1} V_{j-1} has completed
+      if (j > 0 && !waited_o) {
+        mbar_wait(bar(kBarO), (j - 1) & 1);
+        tc_fence_after();
+      }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        if (c * 32 < nk) {
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
             const int chunk = (c * 4 + w) ^ (r & 7);
-            *reinterpret_cast<uint4*>(my_row + (chunk << 4)) = make_uint4(pk[4 * w], pk[4 * w + 1], pk[4 * w + 2], pk[4 * w + 3]);
+            *reinterpret_cast<uint4*>(my_row + (chunk << 4)) =
+                make_uint4(pk[c][4 * w], pk[c][4 * w + 1], pk[c][4 * w + 2], pk[c][4 * w + 3]);
           }
         }
       }
@@ -254,7 +286,9 @@ attn_vit_tc5_kernel(const __grid_constant__ CUtensorMap tm, VitTc5Params p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(kBarP));
+      VCB_STAMP(5);
     }
+#undef VCB_STAMP
 
     // ---- epilogue: O (TMEM) / l  -> fp16
     mbar_wait(bar(kBarO), (nb - 1) & 1);
@@ -315,6 +349,10 @@ int attn_vit_tc5(const AttnPrefillParams& a, cudaStream_t stream) {
   // (verified on B200: profiles/r01_vit_tc5_bringup.log)
   p.v_desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
   p.v_lbo = 0;
+  p.dbg = nullptr;
+  if (const char* e = getenv("VCB_VIT_TRACE")) {  // profiling aid: device buffer of >= 64 int64 (address in hex)
+    p.dbg = reinterpret_cast<long long*>(strtoull(e, nullptr, 16));
+  }
   dim3 grid((a.seq_len + kQ - 1) / kQ, a.n_heads, a.batch);
   KernelScope scope(kCatAttnVit, stream);
   attn_vit_tc5_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tm, p);

@@ -119,20 +119,31 @@ __global__ void __launch_bounds__(kRmsThreads)
 rmsnorm_kernel(const __half* __restrict__ x, const __half* __restrict__ w, __half* __restrict__ y, int H, float eps) {
   __shared__ float scratch[kRmsThreads / 32];
   griddep_launch();
-  griddep_wait();
   const long row = blockIdx.x;
   const int nch = H / 8;
-  const uint4* xr = reinterpret_cast<const uint4*>(x + row * H);
-  float v[kRmsMaxChunks][8];
-  float sq = 0.f;
+  // the norm weight does not depend on the previous kernel: fetch it before the grid-dependency wait so that only ONE
+  // dependent global round trip (the activations) sits on the decode critical path
+  uint4 wq[kRmsMaxChunks];
 #pragma unroll
   for (int i = 0; i < kRmsMaxChunks; ++i) {
     const int c = threadIdx.x + i * kRmsThreads;
-    if (c < nch) {
-      unpack8(xr[c], v[i]);
+    wq[i] = (c < nch) ? __ldg(reinterpret_cast<const uint4*>(w) + c) : make_uint4(0, 0, 0, 0);
+  }
+  griddep_wait();
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * H);
+  uint4 xq[kRmsMaxChunks];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) sq += v[i][j] * v[i][j];
-    }
+  for (int i = 0; i < kRmsMaxChunks; ++i) {
+    const int c = threadIdx.x + i * kRmsThreads;
+    xq[i] = (c < nch) ? xr[c] : make_uint4(0, 0, 0, 0);
+  }
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < kRmsMaxChunks; ++i) {
+    float v[8];
+    unpack8(xq[i], v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sq += v[j] * v[j];
   }
   const float rstd = rsqrtf(block_sum<kRmsThreads>(sq, scratch) / H + eps);
   uint4* yr = reinterpret_cast<uint4*>(y + row * H);
@@ -140,10 +151,11 @@ rmsnorm_kernel(const __half* __restrict__ x, const __half* __restrict__ w, __hal
   for (int i = 0; i < kRmsMaxChunks; ++i) {
     const int c = threadIdx.x + i * kRmsThreads;
     if (c < nch) {
-      float wv[8], o[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(w) + c), wv);
+      float v[8], wv[8], o[8];
+      unpack8(xq[i], v);
+      unpack8(wq[i], wv);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = v[i][j] * rstd * wv[j];
+      for (int j = 0; j < 8; ++j) o[j] = v[j] * rstd * wv[j];
       yr[c] = pack8(o);
     }
   }
@@ -156,7 +168,8 @@ __global__ void rope_kv_kernel(__half* qkv, int T, int H, int n_heads, const flo
                                const int32_t* __restrict__ pos0_dev, __half* k_pool, __half* v_pool,
                                const int32_t* __restrict__ block_table, int max_pages, int PT) {
   griddep_launch();
-  griddep_wait();
+  // position, page and the cos/sin row were fixed before the previous kernel started (the counters are advanced at the end
+  // of a decode step, the block table is uploaded before the step): only the qkv row depends on the predecessor
   const long m = blockIdx.x;
   const int b = static_cast<int>(m / T), tt = static_cast<int>(m % T);
   const int pos = (pos0_dev ? *pos0_dev : pos0) + tt;
@@ -164,11 +177,15 @@ __global__ void rope_kv_kernel(__half* qkv, int T, int H, int n_heads, const flo
   const int slot = pos % PT;
   __half* row = qkv + m * 3L * H;
   const float2* csr = cs + static_cast<long>(pos) * 64;
+  float c[8], s[8];
+  {
+    const int j0 = (threadIdx.x & 7) * 8;  // blockDim is a multiple of 8: a thread always handles the same j0
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float2 v = __ldg(csr + j0 + j); c[j] = v.x; s[j] = v.y; }
+  }
+  griddep_wait();
   for (int i = threadIdx.x; i < n_heads * 8; i += blockDim.x) {
     const int h = i >> 3, j0 = (i & 7) * 8;
-    float c[8], s[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { const float2 v = csr[j0 + j]; c[j] = v.x; s[j] = v.y; }
     // q: in place
     {
       uint4* p1 = reinterpret_cast<uint4*>(row + h * 128 + j0);

@@ -26,6 +26,7 @@ struct AttnPrefillParams {
 int attn_vit(const AttnPrefillParams& p, cudaStream_t stream);       // dispatcher: tcgen05 kernel when it applies
 int attn_vit_tc5(const AttnPrefillParams& p, cudaStream_t stream);   // tcgen05 + TMEM (attn_vit_tc5.cu)
 int attn_vit_legacy(const AttnPrefillParams& p, cudaStream_t stream);  // mma.sync flash attention
+int attn_vit_pair(const AttnPrefillParams& p, cudaStream_t stream);    // tcgen05, two query tiles per CTA (attn_vit_pair.cu)
 int attn_llama_prefill(const AttnPrefillParams& p, cudaStream_t stream);
 
 struct AttnDecodeParams {
