@@ -296,7 +296,7 @@ def run_b200(args):
     e2e_value = tokens / (ms_e2e / 1e3)
 
     # ---- live per-kernel timing of one more step (CUDA events around every launch, graph disabled)
-    roofline, breakdown = None, None
+    roofline, breakdown, phases = None, None, None
     if rank == 0:
         import ctypes as C
         peaks = load_peaks()
@@ -307,6 +307,19 @@ def run_b200(args):
         _lib.check(lib.vcb_profile_read(ms, nl, 8))
         lib.vcb_profile_enable(0)
         breakdown = {c: {"ms": round(float(ms[i]), 3), "launches": int(nl[i])} for i, c in enumerate(_lib.PROFILE_CATEGORIES)}
+        # phase split in production mode (CUDA graph + PDL): towers+prefill vs decode, device-timed
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record(stream)
+        eng.prefill(ids, dev_px[0], dev_px[1], dev_px[2])
+        ev[1].record(stream)
+        eng.decode(N - 1)
+        ev[2].record(stream)
+        torch.cuda.synchronize()
+        phases = {"towers_prefill_ms": round(ev[0].elapsed_time(ev[1]), 3), "decode_ms": round(ev[1].elapsed_time(ev[2]), 3),
+                  "decode_ms_per_step": round(ev[1].elapsed_time(ev[2]) / (N - 1), 4)}
+        step_bytes_all = 2 * (g.llm_layers * (3 * g.llm_hidden ** 2 + g.llm_hidden ** 2 + 3 * g.llm_ffn * g.llm_hidden) + g.llm_vocab * g.llm_hidden) \
+            + B * (Tp + N // 2) * 2 * g.llm_layers * g.llm_hidden * 2
+        phases["decode_step_hbm_GBs"] = round(step_bytes_all / (phases["decode_ms_per_step"] / 1e3) / 1e9, 1)
         tot = sum(v["ms"] for v in breakdown.values())
         for v in breakdown.values():
             v["share"] = round(v["ms"] / tot, 4) if tot else None
@@ -321,7 +334,7 @@ def run_b200(args):
         tp = os.path.join(ROOT, "profiles", "skinny_traffic.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        roofline = {"kernel": "skinny_gemm_kernel (decode weight streaming: qkv/o/gate-up/down/lm_head)", "bound": "hbm",
+        roofline = {"kernel": "skinny_tma_kernel (TMA-fed decode weight streaming: qkv/o/gate-up/down/lm_head)", "bound": "hbm",
                     "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": (ach / peaks["hbm_gbs"]) if ach else None,
                     "traffic": traffic, "peak_source": peaks["source"],
                     "bytes_per_launch_avg": total_bytes / max(1, sk["launches"]), "launches": sk["launches"],
@@ -337,7 +350,7 @@ def run_b200(args):
             "dtype": "f16", "data": "synthetic", "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * N * 4,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernel_breakdown": breakdown,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernel_breakdown": breakdown, "phases": phases,
             "cpu_baseline": cpu, "impl": "b200",
         }
         print(json.dumps(line), flush=True)

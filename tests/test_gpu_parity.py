@@ -257,3 +257,44 @@ def test_decode_equals_prefill_property():
     ids_ext = torch.cat([ids, nxt[:, None]], dim=1)
     pre2 = eng.prefill(ids_ext, images, segs, depths, want_logits=True)
     assert max_abs(lg[0], pre2["logits"]) <= 2e-2
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# real-size shapes (the oracle still finishes in seconds: real ViT-L tower on 2 images; LLaMA-7B / 13B-shaped decoders
+# with few layers behind a tiny tower)
+# ---------------------------------------------------------------------------------------------------------------
+def test_vit_l_tower_real_size():
+    g = synth.PRESETS["vit_l"]
+    sd = synth.make_state_dict(g, seed=0, only_prefix="model.vision_tower.")
+    images = synth.make_pixels(g, 2, 1)
+    eng = Engine(g, max_batch=1, max_seq_len=64)
+    eng.bind(sd)
+    got = eng.tower_forward(images)
+    ref = orc.clip_tower_forward(images, sd, g)
+    assert got.shape == (2, 576, 1024)
+    assert rel_rms(got, ref) <= 4e-3, rel_rms(got, ref)
+
+
+@pytest.mark.parametrize("name,hidden,heads,ffn,layers,batch", [("7b", 4096, 32, 11008, 2, 8), ("13b", 5120, 40, 13824, 1, 4)])
+def test_llama_real_width(name, hidden, heads, ffn, layers, batch):
+    """Decoder at the real 7B / 13B widths (vocab 32000) behind the tiny tower, batch 8 / 4 (configs 3 and 4 per GPU)."""
+    import dataclasses
+    g = dataclasses.replace(synth.PRESETS["tiny"], name=f"tiny-vit+{name}", llm_hidden=hidden, llm_heads=heads, llm_ffn=ffn,
+                            llm_layers=layers, llm_vocab=32000, init_gain=1.0)
+    sd = synth.make_state_dict(g, seed=3)
+    ids = synth.make_prompt_ids(g, batch, seed=3, n_before=6, n_after=5)
+    images, segs, depths = (synth.make_pixels(g, batch, s) for s in (1, 2, 3))
+    n_new = 4
+    eng = Engine(g, max_batch=batch, max_seq_len=128)
+    eng.bind(sd)
+    pre = eng.prefill(ids, images, segs, depths, want_logits=True)
+    dec_ids, dec_logits = eng.decode(n_new - 1, want_logits=True)
+    torch.cuda.synchronize()
+    ref_ids, ref_logits = orc.greedy_generate(ids, sd, g, images, segs, depths, n_new, return_logits=True)
+    got_ids = torch.cat([pre["next_ids"][:, None], dec_ids], dim=1)
+    got_logits = [pre["logits"]] + [dec_logits[s] for s in range(n_new - 1)]
+    assert rel_rms(got_logits[0], ref_logits[0]) <= 4e-3, rel_rms(got_logits[0], ref_logits[0])  # prefill logits
+    alive = check_greedy(got_ids, got_logits, ref_ids, ref_logits, logit_tol=3e-2)  # teacher-forced while ids agree
+    assert bool(alive.any())
+    gen = eng.generate(ids, images, segs, depths, max_new_tokens=n_new)  # CUDA-graph path
+    assert torch.equal(gen, got_ids.cpu().long())

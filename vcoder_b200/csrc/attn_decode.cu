@@ -49,15 +49,39 @@ attn_decode_split_kernel(AttnDecodeParams p, int splits) {
   }
   const int nkeys = min(kChunk, ctx - k0);
 
+  // Fused RoPE (p.cos_sin != null): q arrives un-rotated, and the current token's k / v are taken from the QKV row,
+  // rotated here and appended to the paged cache by the one CTA whose split contains the current position
+  // (modeling_llama.py:124-168 apply_rotary_pos_emb; positions = cache length, vcoder_ds_llava_llama.py:120-142).
+  const bool fuse_rope = p.cos_sin != nullptr;
+  const int pos = ctx - 1;
+  float cs_c[8], cs_s[8];
+  if (fuse_rope) {
+    const float2* csr = p.cos_sin + static_cast<long>(pos) * 64 + (l16 & 7) * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { const float2 v = __ldg(csr + e); cs_c[e] = v.x; cs_s[e] = v.y; }
+  }
+  // rotate-half on a 128-dim row spread over 16 lanes (8 dims each): lane l pairs with lane l^8
+  auto rotate = [&](float* x) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float other = __shfl_xor_sync(0xffffffffu, x[e], 8);
+      x[e] = (l16 < 8) ? (x[e] * cs_c[e] - other * cs_s[e]) : (x[e] * cs_c[e] + other * cs_s[e]);
+    }
+  };
+  const __half* qkv_row = p.q + static_cast<long>(b) * p.q_stride;
   float qf[8];
   {
-    const uint4 qv = *reinterpret_cast<const uint4*>(p.q + static_cast<long>(b) * p.q_stride + h * kDH + l16 * 8);
+    const uint4 qv = *reinterpret_cast<const uint4*>(qkv_row + h * kDH + l16 * 8);
     unpack8(qv, qf);
+    if (fuse_rope) rotate(qf);
     const float sc = p.scale * 1.4426950408889634f;  // scores in the log2 domain
 #pragma unroll
     for (int i = 0; i < 8; ++i) qf[i] *= sc;
   }
   const int32_t* bt = p.block_table + b * p.max_pages + k0 / kPT;
+  // where the current token lives inside this split (only meaningful when pos is in [k0, k0 + nkeys))
+  const bool own_pos = fuse_rope && pos >= k0 && pos < k0 + kChunk;
+  const int pos_tile = (pos - k0) / kPT, pos_slot = (pos - k0) % kPT;
 
   float m = -INFINITY, l = 0.f;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -67,17 +91,37 @@ attn_decode_split_kernel(AttnDecodeParams p, int splits) {
     const __half* kb = p.k_pool + page_off;
     const __half* vb = p.v_pool + page_off;
     uint4 kv[8], vv[8];
+    const bool fresh_tile = own_pos && t == pos_tile;  // CTA-uniform
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int slot = hw + 8 * i;
-      const bool ok = t * kPT + slot < nkeys;
+      const bool ok = t * kPT + slot < nkeys && !(fresh_tile && slot == pos_slot);
       kv[i] = ok ? ldg_stream16(kb + slot * kDH) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int slot = hw + 8 * i;
-      const bool ok = t * kPT + slot < nkeys;
+      const bool ok = t * kPT + slot < nkeys && !(fresh_tile && slot == pos_slot);
       vv[i] = ok ? ldg_stream16(vb + slot * kDH) : make_uint4(0, 0, 0, 0);
+    }
+    if (fresh_tile && (tid >> 5) == ((pos_slot & 7) >> 1)) {  // the warp that holds the owning half-warp (warp-uniform)
+      // current token: k (rotated) and v come from the QKV row and are appended to the cache here
+      const int H = p.n_heads * kDH;
+      uint4 kraw = *reinterpret_cast<const uint4*>(qkv_row + H + h * kDH + l16 * 8);
+      const uint4 vraw = *reinterpret_cast<const uint4*>(qkv_row + 2 * H + h * kDH + l16 * 8);
+      float kf[8];
+      unpack8(kraw, kf);
+      rotate(kf);
+      kraw = make_uint4(pack_half2(kf[0], kf[1]), pack_half2(kf[2], kf[3]), pack_half2(kf[4], kf[5]), pack_half2(kf[6], kf[7]));
+      if (hw == (pos_slot & 7)) {
+        const int i_own = pos_slot >> 3;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (i == i_own) { kv[i] = kraw; vv[i] = vraw; }
+        }
+        *reinterpret_cast<uint4*>(p.k_pool_w + page_off + static_cast<long>(pos_slot) * kDH) = kraw;
+        *reinterpret_cast<uint4*>(p.v_pool_w + page_off + static_cast<long>(pos_slot) * kDH) = vraw;
+      }
     }
     float s[8];
     float mt = -INFINITY;

@@ -274,7 +274,7 @@ int attn_vit(const AttnPrefillParams& p, cudaStream_t stream) {
   if (use_tc5 < 0) {
     const char* e = getenv("VCB_VIT_ATTN");
     const std::string v = e ? e : "";
-    use_tc5 = v == "legacy" ? 0 : (v == "pair" ? 2 : 1);
+    use_tc5 = v == "legacy" ? 0 : (v == "tc5" ? 1 : 2);  // default: pair schedule (fastest measured)
   }
   const bool packed = p.q_stride == p.kv_stride && p.k == p.q + p.n_heads * 64 && p.v == p.q + 2 * p.n_heads * 64;
   if (use_tc5 == 2 && packed && p.q_stride % 8 == 0) return attn_vit_pair(p, stream);

@@ -7,6 +7,7 @@
 #include "engine.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace vcb {
@@ -672,21 +673,30 @@ int decode_step_launch(Engine* e, int max_ctx, cudaStream_t st) {
   __half* xn = e->xnd.as<__half>();
   __half* qkv = e->qkvd.as<__half>();
   const size_t layer_pool = static_cast<size_t>(e->n_pages) * c.llm_heads * c.kv_page_tokens * 128;
+  static int fuse_env = -1;  // VCB_FUSE_NORM=1 fuses RMSNorm into the skinny GEMMs (kept for A/B; default: separate kernels)
+  if (fuse_env < 0) { const char* ev = getenv("VCB_FUSE_NORM"); fuse_env = ev ? atoi(ev) : 0; }  // measured slower on B200 (3.2 vs 5.2 TB/s): off
+  const bool fuse_norm = fuse_env != 0;
+  static int rope_env = -1;  // RoPE + KV append fused into the decode attention kernel (VCB_FUSE_ROPE=0: separate kernel)
+  if (rope_env < 0) { const char* ev = getenv("VCB_FUSE_ROPE"); rope_env = ev ? atoi(ev) : 1; }
+  const bool fuse_rope = rope_env != 0;
   VCB_TRY(embed_gather(e->next_ids.as<int32_t>(), e->embed.as<__half>(), x, B, H, st));
   for (int li = 0; li < c.llm_layers; ++li) {
     const LlmLayerW& l = e->llm[li];
     __half* kp = e->k_pool.as<__half>() + li * layer_pool;
     __half* vp = e->v_pool.as<__half>() + li * layer_pool;
-    VCB_TRY(rmsnorm_f16(x, l.ln1.as<__half>(), xn, B, H, c.llm_rms_eps, st));
+    if (!fuse_norm) VCB_TRY(rmsnorm_f16(x, l.ln1.as<__half>(), xn, B, H, c.llm_rms_eps, st));
     {
       SkinnyParams s;
-      s.X = xn; s.ldx = H; s.W = l.qkv_w.as<__half>(); s.Y = qkv; s.ldy = 3 * H; s.B = B; s.N = 3 * H; s.K = H;
+      if (fuse_norm) { s.norm_w = l.ln1.as<__half>(); s.norm_eps = c.llm_rms_eps; }
+      s.X = fuse_norm ? x : xn; s.ldx = H; s.W = l.qkv_w.as<__half>(); s.Y = qkv; s.ldy = 3 * H; s.B = B; s.N = 3 * H; s.K = H;
       VCB_TRY(skinny_gemm(s, st));
     }
-    VCB_TRY(rope_kv_write(qkv, B, 1, H, c.llm_heads, e->rope.as<float2>(), 0, counters, kp, vp,
-                          e->block_table.as<int32_t>(), e->max_pages_per_seq, c.kv_page_tokens, st));
+    if (!fuse_rope)
+      VCB_TRY(rope_kv_write(qkv, B, 1, H, c.llm_heads, e->rope.as<float2>(), 0, counters, kp, vp,
+                            e->block_table.as<int32_t>(), e->max_pages_per_seq, c.kv_page_tokens, st));
     {
       AttnDecodeParams a;
+      if (fuse_rope) { a.cos_sin = e->rope.as<float2>(); a.k_pool_w = kp; a.v_pool_w = vp; }
       a.q = qkv; a.q_stride = 3 * H; a.k_pool = kp; a.v_pool = vp;
       a.block_table = e->block_table.as<int32_t>(); a.max_pages = e->max_pages_per_seq; a.page_tokens = c.kv_page_tokens;
       a.ctx_len = counters + 2;  // cache_len + 1 (the current token attends to itself)
@@ -701,10 +711,11 @@ int decode_step_launch(Engine* e, int max_ctx, cudaStream_t st) {
       s.B = B; s.N = H; s.K = H;
       VCB_TRY(skinny_gemm(s, st));
     }
-    VCB_TRY(rmsnorm_f16(x, l.ln2.as<__half>(), xn, B, H, c.llm_rms_eps, st));
+    if (!fuse_norm) VCB_TRY(rmsnorm_f16(x, l.ln2.as<__half>(), xn, B, H, c.llm_rms_eps, st));
     {
       SkinnyParams s;
-      s.X = xn; s.ldx = H; s.W = l.gu_w.as<__half>(); s.Y = e->midd.as<__half>(); s.ldy = FF; s.B = B; s.N = 2 * FF;
+      if (fuse_norm) { s.norm_w = l.ln2.as<__half>(); s.norm_eps = c.llm_rms_eps; }
+      s.X = fuse_norm ? x : xn; s.ldx = H; s.W = l.gu_w.as<__half>(); s.Y = e->midd.as<__half>(); s.ldy = FF; s.B = B; s.N = 2 * FF;
       s.K = H; s.swiglu = 1;
       VCB_TRY(skinny_gemm(s, st));
     }
@@ -715,10 +726,11 @@ int decode_step_launch(Engine* e, int max_ctx, cudaStream_t st) {
       VCB_TRY(skinny_gemm(s, st));
     }
   }
-  VCB_TRY(rmsnorm_f16(x, e->final_norm.as<__half>(), xn, B, H, c.llm_rms_eps, st));
+  if (!fuse_norm) VCB_TRY(rmsnorm_f16(x, e->final_norm.as<__half>(), xn, B, H, c.llm_rms_eps, st));
   {
     SkinnyParams s;
-    s.X = xn; s.ldx = H; s.W = e->lm_head.as<__half>(); s.Y = e->logits.as<__half>(); s.ldy = V; s.B = B; s.N = V; s.K = H;
+    if (fuse_norm) { s.norm_w = e->final_norm.as<__half>(); s.norm_eps = c.llm_rms_eps; }
+    s.X = fuse_norm ? x : xn; s.ldx = H; s.W = e->lm_head.as<__half>(); s.Y = e->logits.as<__half>(); s.ldy = V; s.B = B; s.N = V; s.K = H;
     VCB_TRY(skinny_gemm(s, st));
   }
   VCB_TRY(argmax_rows(e->logits.as<__half>(), B, V, e->next_ids.as<int32_t>(), e->trace.as<int32_t>(), c.max_seq_len,

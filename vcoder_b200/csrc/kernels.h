@@ -38,6 +38,11 @@ struct AttnDecodeParams {
   int max_pages = 0, page_tokens = 0;
   const int32_t* ctx_len = nullptr;  // device scalar: number of cached tokens INCLUDING the current one
   int max_ctx = 0;                   // host upper bound used to size the grid
+  // fused RoPE + KV append (decode): q is un-rotated, k/v of the current token are read from the QKV row (k at +H,
+  // v at +2H), rotated with cos_sin[pos] and written to the cache by the attention kernel itself
+  const float2* cos_sin = nullptr;
+  __half* k_pool_w = nullptr;
+  __half* v_pool_w = nullptr;
   float* part_o = nullptr;           // [B*heads, splits, 128]
   float* part_ml = nullptr;          // [B*heads, splits, 2]
   __half* out = nullptr;             // [B, H]

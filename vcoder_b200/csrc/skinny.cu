@@ -246,7 +246,7 @@ int skinny_gemm(const SkinnyParams& p, cudaStream_t stream) {
   {
     static int impl = -1;  // 0 = LDG kernel (this file), 1 = TMA-fed kernel (skinny_tma.cu)
     if (impl < 0) { const char* e = getenv("VCB_SKINNY_IMPL"); impl = (e && std::string(e) == "ldg") ? 0 : 1; }  // default: TMA-fed (measured faster)
-    if (impl == 1 && p.K % 64 == 0 && p.norm_w == nullptr) return skinny_gemm_tma(p, stream);
+    if (impl == 1 && p.K % 64 == 0) return skinny_gemm_tma(p, stream);
   }
   VCB_CHECK(p.B >= 1 && p.B <= 32, kErrInvalid, "skinny_gemm: batch must be in [1, 32]");
   VCB_CHECK(p.N % 16 == 0 && p.K % 32 == 0, kErrInvalid, "skinny_gemm: N % 16 and K % 32 must be 0");

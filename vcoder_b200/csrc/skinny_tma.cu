@@ -28,6 +28,10 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
   return r;
 }
+__device__ __forceinline__ uint32_t hmul2_u32(uint32_t a, uint32_t b) {
+  __half2 r = __hmul2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + fast_exp2(-1.4426950408889634f * x)); }
 
 // W viewed as a 3-D tensor [K/64][N][64]: dim0 = k within a 64-block, dim1 = row, dim2 = k-block
@@ -40,6 +44,7 @@ skinny_tma_kernel(const __grid_constant__ CUtensorMap tmW, SkinnyParams p) {
   RedT* red = reinterpret_cast<RedT*>(smem + WARPS * kDepth * kStageBytes);
   typedef uint64_t BarT[kDepth];
   BarT* bars = reinterpret_cast<BarT*>(smem + WARPS * kDepth * kStageBytes + sizeof(RedT) * WARPS + 8);
+  float* s_ssq = reinterpret_cast<float*>(smem + WARPS * kDepth * kStageBytes + sizeof(RedT) * WARPS + 8 + sizeof(BarT) * WARPS);  // [WARPS][8*NB]
   griddep_launch();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -77,6 +82,10 @@ skinny_tma_kernel(const __grid_constant__ CUtensorMap tmW, SkinnyParams p) {
 #pragma unroll
   for (int nb = 0; nb < NB; ++nb) { acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f; }
 
+  float ssq[NB];
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb) ssq[nb] = 0.f;
+  const bool fuse_norm = p.norm_w != nullptr;
   const uint32_t r_lo = static_cast<uint32_t>(g) * 128, r_hi = static_cast<uint32_t>(g + 8) * 128;
   for (int i = 0; i < my_groups; ++i) {
     const int s = i % kDepth;
@@ -90,6 +99,21 @@ skinny_tma_kernel(const __grid_constant__ CUtensorMap tmW, SkinnyParams p) {
       for (int nb = 0; nb < NB; ++nb) {
         const int k = k0 + c * 32;
         xv[c][nb] = (xok[nb] && k < p.K) ? __ldg(reinterpret_cast<const uint4*>(xrow[nb] + k)) : make_uint4(0, 0, 0, 0);
+      }
+      if (fuse_norm && k0 + c * 32 < p.K) {
+        // fused LlamaRMSNorm: y = rstd * W (x o w_norm).  The weight stream is driven by the TMA ring, so this extra
+        // ALU work overlaps the wait for the next stage instead of delaying loads (unlike in the LDG kernel).
+        const uint4 wn = __ldg(reinterpret_cast<const uint4*>(p.norm_w + k0 + c * 32 + t * 8));
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+          const float2 a = unpack_half2(xv[c][nb].x), b2 = unpack_half2(xv[c][nb].y), c2 = unpack_half2(xv[c][nb].z),
+                       d2 = unpack_half2(xv[c][nb].w);
+          ssq[nb] += a.x * a.x + a.y * a.y + b2.x * b2.x + b2.y * b2.y + c2.x * c2.x + c2.y * c2.y + d2.x * d2.x + d2.y * d2.y;
+          xv[c][nb].x = hmul2_u32(xv[c][nb].x, wn.x);
+          xv[c][nb].y = hmul2_u32(xv[c][nb].y, wn.y);
+          xv[c][nb].z = hmul2_u32(xv[c][nb].z, wn.z);
+          xv[c][nb].w = hmul2_u32(xv[c][nb].w, wn.w);
+        }
       }
     }
     mbar_wait(smem_u32(&bars[warp][s]), ph);
@@ -126,7 +150,23 @@ skinny_tma_kernel(const __grid_constant__ CUtensorMap tmW, SkinnyParams p) {
     red[warp][g + 8][nb * 8 + 2 * t] = acc[nb][2];
     red[warp][g + 8][nb * 8 + 2 * t + 1] = acc[nb][3];
   }
+  if (fuse_norm) {
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+      float v = ssq[nb];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      if (t == 0) s_ssq[warp * 8 * NB + nb * 8 + g] = v;
+    }
+  }
   __syncthreads();
+  auto rstd_of = [&](int n) -> float {
+    if (!fuse_norm) return 1.f;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) v += s_ssq[w * 8 * NB + n];
+    return rsqrtf(v / static_cast<float>(p.K) + p.norm_eps);
+  };
   constexpr int kThreads = WARPS * 32;
   if (p.swiglu) {
     for (int idx = tid; idx < 8 * 8 * NB; idx += kThreads) {
@@ -135,6 +175,9 @@ skinny_tma_kernel(const __grid_constant__ CUtensorMap tmW, SkinnyParams p) {
         float gate = 0.f, up = 0.f;
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) { gate += red[w][e][n]; up += red[w][e + 8][n]; }
+        const float rs = rstd_of(n);
+        gate *= rs;
+        up *= rs;
         p.Y[static_cast<long>(n) * p.ldy + blockIdx.x * 8 + e] = __float2half_rn(silu_f(gate) * up);
       }
     }
@@ -145,6 +188,7 @@ skinny_tma_kernel(const __grid_constant__ CUtensorMap tmW, SkinnyParams p) {
         float v = 0.f;
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) v += red[w][r][n];
+        v *= rstd_of(n);
         if (p.residual) v += __half2float(p.residual[static_cast<long>(n) * p.ldr + row0 + r]);
         p.Y[static_cast<long>(n) * p.ldy + row0 + r] = __float2half_rn(v);
       }
@@ -155,7 +199,7 @@ skinny_tma_kernel(const __grid_constant__ CUtensorMap tmW, SkinnyParams p) {
 template <int NB, int WARPS, int kDepth, int kGroup>
 int launch_tma(const CUtensorMap& tm, const SkinnyParams& p, int grid, cudaStream_t stream) {
   constexpr int kStageBytes = kGroup * 16 * kKBlk * 2;
-  constexpr int smem = WARPS * kDepth * kStageBytes + WARPS * 16 * (8 * NB + 1) * 4 + 8 + WARPS * kDepth * 8 + 16;
+  constexpr int smem = WARPS * kDepth * kStageBytes + WARPS * 16 * (8 * NB + 1) * 4 + 8 + WARPS * kDepth * 8 + WARPS * 8 * NB * 4 + 16;
   static_assert(smem <= 227 * 1024, "skinny_tma: ring does not fit in shared memory");
   static bool attr = false;
   if (!attr) {
@@ -189,7 +233,6 @@ int make_tmap_w3d(CUtensorMap* m, const void* ptr, uint64_t K, uint64_t N, uint3
 int skinny_gemm_tma(const SkinnyParams& p, cudaStream_t stream) {
   VCB_CHECK(p.B >= 1 && p.B <= 32, kErrInvalid, "skinny_gemm: batch must be in [1, 32]");
   VCB_CHECK(p.N % 16 == 0 && p.K % 64 == 0, kErrInvalid, "skinny_gemm_tma: N % 16 and K % 64 must be 0");
-  VCB_CHECK(p.norm_w == nullptr, kErrInvalid, "skinny_gemm_tma: fused norm is only in the LDG kernel");
   const int grid = p.N / 16;
   const int nb = (p.B + 7) / 8;
   int warps = 4;  // 4 warps x 3 stages x 8 KiB = 96 KiB per CTA -> two CTAs per SM
