@@ -78,44 +78,52 @@ skinny_tma_kernel(const __grid_constant__ CUtensorMap tmW, SkinnyParams p) {
     xok[nb] = (nb * 8 + g) < p.B;
     xrow[nb] = p.X + static_cast<long>(xok[nb] ? nb * 8 + g : 0) * p.ldx + t * 8;
   }
-  float acc[NB][4];
+  // four independent accumulator sets per batch tile: consecutive 32-k chunks go to different sets, so the mma.sync
+  // dependency chain per stage is 4 deep instead of 16 (summed once at the end)
+  constexpr int kAcc = 4;
+  float acc[NB][kAcc][4];
 #pragma unroll
-  for (int nb = 0; nb < NB; ++nb) { acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f; }
+  for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+    for (int a = 0; a < kAcc; ++a) { acc[nb][a][0] = acc[nb][a][1] = acc[nb][a][2] = acc[nb][a][3] = 0.f; }
 
   float ssq[NB];
 #pragma unroll
   for (int nb = 0; nb < NB; ++nb) ssq[nb] = 0.f;
   const bool fuse_norm = p.norm_w != nullptr;
   const uint32_t r_lo = static_cast<uint32_t>(g) * 128, r_hi = static_cast<uint32_t>(g + 8) * 128;
-  for (int i = 0; i < my_groups; ++i) {
-    const int s = i % kDepth;
-    const uint32_t ph = static_cast<uint32_t>((i / kDepth) & 1);
+
+  // X fragments of one k-group (8 chunks of 32 k), optionally with the fused RMSNorm weight folded in
+  auto load_x = [&](int i, uint4 (&dst)[2 * kGroup][NB]) {
     const int k0 = (g_begin + i) * kGroup * kKBlk;
-    // X for the 8 32-k chunks of this group (issued before the barrier wait so they overlap it)
-    uint4 xv[2 * kGroup][NB];
 #pragma unroll
     for (int c = 0; c < 2 * kGroup; ++c) {
+      const int k = k0 + c * 32;
 #pragma unroll
-      for (int nb = 0; nb < NB; ++nb) {
-        const int k = k0 + c * 32;
-        xv[c][nb] = (xok[nb] && k < p.K) ? __ldg(reinterpret_cast<const uint4*>(xrow[nb] + k)) : make_uint4(0, 0, 0, 0);
-      }
-      if (fuse_norm && k0 + c * 32 < p.K) {
-        // fused LlamaRMSNorm: y = rstd * W (x o w_norm).  The weight stream is driven by the TMA ring, so this extra
-        // ALU work overlaps the wait for the next stage instead of delaying loads (unlike in the LDG kernel).
-        const uint4 wn = __ldg(reinterpret_cast<const uint4*>(p.norm_w + k0 + c * 32 + t * 8));
+      for (int nb = 0; nb < NB; ++nb)
+        dst[c][nb] = (xok[nb] && k < p.K) ? __ldg(reinterpret_cast<const uint4*>(xrow[nb] + k)) : make_uint4(0, 0, 0, 0);
+      if (fuse_norm && k < p.K) {
+        const uint4 wn = __ldg(reinterpret_cast<const uint4*>(p.norm_w + k + t * 8));
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) {
-          const float2 a = unpack_half2(xv[c][nb].x), b2 = unpack_half2(xv[c][nb].y), c2 = unpack_half2(xv[c][nb].z),
-                       d2 = unpack_half2(xv[c][nb].w);
+          const float2 a = unpack_half2(dst[c][nb].x), b2 = unpack_half2(dst[c][nb].y), c2 = unpack_half2(dst[c][nb].z),
+                       d2 = unpack_half2(dst[c][nb].w);
           ssq[nb] += a.x * a.x + a.y * a.y + b2.x * b2.x + b2.y * b2.y + c2.x * c2.x + c2.y * c2.y + d2.x * d2.x + d2.y * d2.y;
-          xv[c][nb].x = hmul2_u32(xv[c][nb].x, wn.x);
-          xv[c][nb].y = hmul2_u32(xv[c][nb].y, wn.y);
-          xv[c][nb].z = hmul2_u32(xv[c][nb].z, wn.z);
-          xv[c][nb].w = hmul2_u32(xv[c][nb].w, wn.w);
+          dst[c][nb].x = hmul2_u32(dst[c][nb].x, wn.x);
+          dst[c][nb].y = hmul2_u32(dst[c][nb].y, wn.y);
+          dst[c][nb].z = hmul2_u32(dst[c][nb].z, wn.z);
+          dst[c][nb].w = hmul2_u32(dst[c][nb].w, wn.w);
         }
       }
     }
+  };
+
+  uint4 xv[2 * kGroup][NB], xnext[2 * kGroup][NB];
+  if (my_groups > 0) load_x(0, xv);
+  for (int i = 0; i < my_groups; ++i) {
+    const int s = i % kDepth;
+    const uint32_t ph = static_cast<uint32_t>((i / kDepth) & 1);
+    if (i + 1 < my_groups) load_x(i + 1, xnext);  // next group's activations travel while this stage is consumed
     mbar_wait(smem_u32(&bars[warp][s]), ph);
     const uint32_t st = ring + s * kStageBytes;
 #pragma unroll
@@ -126,12 +134,15 @@ skinny_tma_kernel(const __grid_constant__ CUtensorMap tmW, SkinnyParams p) {
         const uint32_t ch = static_cast<uint32_t>(4 * hlf + t);
         const uint4 wl = lds128(st + kb * 2048 + r_lo + ((ch ^ static_cast<uint32_t>(g & 7)) << 4));
         const uint4 wh = lds128(st + kb * 2048 + r_hi + ((ch ^ static_cast<uint32_t>((g + 8) & 7)) << 4));
+        constexpr int kA0 = 0;
+        const int a0 = (kb * 2 + hlf) & (kAcc - 1);
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) {
           const uint4 x = xv[kb * 2 + hlf][nb];
-          mma_16816(acc[nb], wl.x, wh.x, wl.y, wh.y, x.x, x.y);
-          mma_16816(acc[nb], wl.z, wh.z, wl.w, wh.w, x.z, x.w);
+          mma_16816(acc[nb][a0], wl.x, wh.x, wl.y, wh.y, x.x, x.y);
+          mma_16816(acc[nb][(a0 + 2) & (kAcc - 1)], wl.z, wh.z, wl.w, wh.w, x.z, x.w);
         }
+        (void)kA0;
       }
     }
     __syncwarp();  // every lane is done with stage s before it is refilled
@@ -140,15 +151,27 @@ skinny_tma_kernel(const __grid_constant__ CUtensorMap tmW, SkinnyParams p) {
       mbar_expect_tx(b, kStageBytes);
       tma_load_3d(st, &tmW, b, 0, row0, (g_begin + i + kDepth) * kGroup);
     }
+    if (i + 1 < my_groups) {
+#pragma unroll
+      for (int c = 0; c < 2 * kGroup; ++c)
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) xv[c][nb] = xnext[c][nb];
+    }
   }
+  // fold the accumulator sets
+  float accs[NB][4];
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) accs[nb][j] = (acc[nb][0][j] + acc[nb][1][j]) + (acc[nb][2][j] + acc[nb][3][j]);
 
   // cross-warp (split-K) reduction through shared memory
 #pragma unroll
   for (int nb = 0; nb < NB; ++nb) {
-    red[warp][g][nb * 8 + 2 * t] = acc[nb][0];
-    red[warp][g][nb * 8 + 2 * t + 1] = acc[nb][1];
-    red[warp][g + 8][nb * 8 + 2 * t] = acc[nb][2];
-    red[warp][g + 8][nb * 8 + 2 * t + 1] = acc[nb][3];
+    red[warp][g][nb * 8 + 2 * t] = accs[nb][0];
+    red[warp][g][nb * 8 + 2 * t + 1] = accs[nb][1];
+    red[warp][g + 8][nb * 8 + 2 * t] = accs[nb][2];
+    red[warp][g + 8][nb * 8 + 2 * t + 1] = accs[nb][3];
   }
   if (fuse_norm) {
 #pragma unroll
