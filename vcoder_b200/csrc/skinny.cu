@@ -241,12 +241,19 @@ int launch_sk_w(const SkinnyParams& p, int grid, int warps, cudaStream_t stream)
 }  // namespace
 
 int skinny_gemm_tma(const SkinnyParams& p, cudaStream_t stream);
+int skinny_gemm_tc5(const SkinnyParams& p, cudaStream_t stream);
+bool skinny_tc5_supported(const SkinnyParams& p);
 
 int skinny_gemm(const SkinnyParams& p, cudaStream_t stream) {
   {
-    static int impl = -1;  // 0 = LDG kernel (this file), 1 = TMA-fed kernel (skinny_tma.cu)
-    if (impl < 0) { const char* e = getenv("VCB_SKINNY_IMPL"); impl = (e && std::string(e) == "ldg") ? 0 : 1; }  // default: TMA-fed (measured faster)
-    if (impl == 1 && p.K % 64 == 0) return skinny_gemm_tma(p, stream);
+    static int impl = -1;  // 0 = LDG kernel (this file), 1 = TMA-fed mma.sync kernel (skinny_tma.cu), 2 = tcgen05 (skinny_tc5.cu)
+    if (impl < 0) {
+      const char* e = getenv("VCB_SKINNY_IMPL");
+      const std::string v = e ? e : "";
+      impl = v == "ldg" ? 0 : (v == "tc5" ? 2 : 1);
+    }
+    if (impl == 2 && skinny_tc5_supported(p)) return skinny_gemm_tc5(p, stream);
+    if (impl >= 1 && p.K % 64 == 0) return skinny_gemm_tma(p, stream);
   }
   VCB_CHECK(p.B >= 1 && p.B <= 32, kErrInvalid, "skinny_gemm: batch must be in [1, 32]");
   VCB_CHECK(p.N % 16 == 0 && p.K % 32 == 0, kErrInvalid, "skinny_gemm: N % 16 and K % 32 must be 0");
