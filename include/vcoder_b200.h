@@ -125,6 +125,15 @@ int vcb_op_rmsnorm_f16(const vcb_half* x_dev, const vcb_half* w_dev, vcb_half* y
 int vcb_op_attention_vit_f16(const vcb_half* qkv_dev, int32_t B, int32_t S, int32_t heads, float scale,
                              vcb_half* out_dev, void* stream);
 
+/* HF GenerationMixin.sample() on a batch of fp16 logit rows [B,V] (V <= 32768): scores / temperature ->
+ * TopKLogitsWarper(top_k; 0 = off; ties with the k-th score are kept) -> TopPLogitsWarper(top_p) -> softmax -> one draw per
+ * row (transformers/generation/logits_process.py, generation/utils.py sample(); reached from serve/cli.py:121-132 with
+ * do_sample=True).  The draw is the inverse CDF of the filtered distribution, in descending-score order (index ascending
+ * among equal scores), at u = vcb_philox_uniform(seed, step, row).  kept_dev (optional) receives the number of tokens
+ * that survived the filters per row. */
+int vcb_op_sample_f16(const vcb_half* logits_dev, int32_t B, int32_t V, float temperature, int32_t top_k, float top_p,
+                      uint64_t seed, int32_t step, int32_t* next_ids_dev, int32_t* kept_dev, void* stream);
+
 /* ---- host-only logic ------------------------------------------------------------------------ */
 
 /* The splice plan of prepare_inputs_labels_for_multimodal (vcoder_ds_llava_arch.py:175-312 /
@@ -134,6 +143,10 @@ int vcb_op_attention_vit_f16(const vcb_half* qkv_dev, int32_t B, int32_t S, int3
  *   each image is the CLS token and is never referenced).  Needs no GPU. */
 int vcb_splice_plan(int32_t variant, const int64_t* ids_host, int32_t B, int32_t T, int32_t n_patches, int32_t has_seg,
                     const uint8_t* depth_nonzero_host, int32_t* plan_out, int64_t plan_cap, int32_t* out_len);
+
+/* The uniform in [0,1) the sampler uses for (seed, step = index of the token since the prompt, row = sequence in the
+ * batch): top 24 bits of the first word of Philox4x32-10 with key = seed, counter = (step, row, 0, 0).  Needs no GPU. */
+float vcb_philox_uniform(uint64_t seed, uint32_t step, uint32_t row);
 
 /* ---- engine --------------------------------------------------------------------------------- */
 
@@ -177,6 +190,23 @@ int vcb_decode(vcb_handle h, int32_t n_steps, int32_t* out_ids_any, vcb_half* lo
 int vcb_generate(vcb_handle h, const int64_t* ids_host, int32_t B, int32_t T, const vcb_half* images_any,
                  const vcb_half* segs_any, const vcb_half* depths_any, int32_t max_new_tokens, int64_t* out_ids_host,
                  void* stream);
+
+/* generate(do_sample=, temperature=, top_k=, top_p=) for the following vcb_prefill / vcb_decode* / vcb_generate calls on
+ * this handle (serve/cli.py:121-132 passes do_sample=True, temperature; serve/chat.py:141-151 adds top_p; top_k = 50 is
+ * the GenerationConfig default).  do_sample = 0 restores greedy argmax.  Invalid values fail with VCB_ERR_INVALID and
+ * the message HF's warpers raise (ValueError in the shim). */
+int vcb_set_sampling(vcb_handle h, int32_t do_sample, float temperature, int32_t top_k, float top_p, uint64_t seed,
+                     void* stream);
+
+/* Per-token streaming decode for TextStreamer / KeywordsStoppingCriteria / eos handling (serve/cli.py:117-132,
+ * mm_utils.py:128-151, serve/chat.py:131-159): up to max_steps tokens; `lookahead` (1..16) decode steps stay queued on
+ * the GPU while `cb(user, step, ids_host[B], B)` runs for the token of step `step` (0-based within this call).  A
+ * non-zero return stops after that token: the steps already queued are discarded and the KV length / RNG step are
+ * rolled back, so a later vcb_decode* continues right after the accepted token.  *n_accepted = tokens delivered.
+ * Synchronous. */
+typedef int (*vcb_token_callback)(void* user, int32_t step, const int32_t* ids_host, int32_t B);
+int vcb_decode_stream(vcb_handle h, int32_t max_steps, int32_t lookahead, vcb_token_callback cb, void* user,
+                      int32_t* n_accepted, void* stream);
 
 /* Drops the KV cache contents (pages return to the pool). */
 int vcb_reset(vcb_handle h);

@@ -330,3 +330,82 @@ def greedy_generate(ids, sd, g, images, segs, depths, max_new_tokens: int, retur
             logits = llama_forward(emb[nxt][:, None, :], sd, g, cache)
     ids_out = torch.stack(out, dim=1)
     return (ids_out, trace) if return_logits else ids_out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# f1: do_sample=True — HF GenerationMixin.sample() as reached from serve/cli.py:121-132 / serve/chat.py:141-151
+# (third-party: transformers/generation/logits_process.py Temperature / TopK / TopP warpers, generation/utils.py).
+# tests/test_oracle_golden.py pins sample_filter against the installed transformers warper classes.
+# ---------------------------------------------------------------------------------------------------------
+_M32 = 0xFFFFFFFF
+
+
+def philox_uniform(seed: int, step: int, row: int) -> float:
+    """u in [0,1): top 24 bits of word 0 of Philox4x32-10 (Salmon et al., SC'11), key = seed (lo, hi), counter =
+    (step, row, 0, 0).  torch.multinomial's own stream cannot be reproduced across devices, so the product draws
+    from the SAME filtered distribution by inverse CDF at this u (include/vcoder_b200.h: vcb_philox_uniform)."""
+    k0, k1 = seed & _M32, (seed >> 32) & _M32
+    x0, x1, x2, x3 = step & _M32, row & _M32, 0, 0
+    for _ in range(10):
+        p0, p1 = 0xD2511F53 * x0, 0xCD9E8D57 * x2
+        hi0, lo0, hi1, lo1 = p0 >> 32, p0 & _M32, p1 >> 32, p1 & _M32
+        x0, x1, x2, x3 = hi1 ^ x1 ^ k0, lo1, hi0 ^ x3 ^ k1, lo0
+        k0, k1 = (k0 + 0x9E3779B9) & _M32, (k1 + 0xBB67AE85) & _M32
+    return (x0 >> 8) / 16777216.0
+
+
+def sample_filter(logits: torch.Tensor, temperature: float, top_k: int, top_p: float):
+    """One row of logits [V] -> (order, cdf): `order` = indices of the surviving tokens by descending score (index
+    ascending among equal scores — one valid outcome of torch.sort's unstable order), `cdf` = their inclusive
+    cumulative probability (float64) after TemperatureLogitsWarper -> TopKLogitsWarper -> TopPLogitsWarper -> softmax."""
+    s = logits.detach().to(torch.float64) / float(temperature)
+    V = s.numel()
+    keep = torch.ones(V, dtype=torch.bool)
+    if top_k and top_k > 0:
+        kth = torch.topk(s, min(top_k, V)).values[-1]
+        keep &= ~(s < kth)  # TopKLogitsWarper: scores < k-th largest are removed, ties stay
+    idx = torch.arange(V)
+    order = sorted(idx[keep].tolist(), key=lambda i: (-float(s[i]), i))
+    order = torch.tensor(order, dtype=torch.int64)
+    p = torch.softmax(s[order], dim=0)
+    if top_p is not None and top_p < 1.0:
+        # TopPLogitsWarper on the ascending sort: removed while cumsum_asc <= 1 - top_p  <=>  kept while the mass of the
+        # higher-ranked tokens is < top_p; the top token always stays (min_tokens_to_keep = 1)
+        before = torch.cumsum(p, 0) - p
+        n = max(1, int((before < top_p).sum()))
+        order, p = order[:n], p[:n]
+        p = p / p.sum()
+    return order, torch.cumsum(p, 0)
+
+
+def sample_token(logits: torch.Tensor, temperature: float, top_k: int, top_p: float, u: float):
+    """-> (token, margin): inverse-CDF draw at u; margin = distance of u from the nearest CDF edge (tests skip exact
+    token equality when it is below the fp32 round-off of the device scan)."""
+    order, cdf = sample_filter(logits, temperature, top_k, top_p)
+    pick = int((cdf <= u).sum())
+    pick = min(pick, order.numel() - 1)
+    edges = torch.cat([torch.zeros(1, dtype=cdf.dtype), cdf])
+    margin = float((edges - u).abs().min())
+    return int(order[pick]), margin
+
+
+def sample_generate(ids, sd, g, images, segs, depths, max_new_tokens: int, temperature: float, top_k: int,
+                    top_p: float, seed: int, return_logits: bool = False):
+    """greedy_generate with the argmax replaced by sample_token at u = philox_uniform(seed, step, row)."""
+    x = prefill_embeds(ids, sd, g, images, segs, depths)
+    cache = KVCache(g.llm_layers)
+    emb = _f(sd["model.embed_tokens.weight"])
+    out, trace, margins = [], [], []
+    logits = llama_forward(x, sd, g, cache)
+    for step in range(max_new_tokens):
+        if return_logits:
+            trace.append(logits)
+        picks = [sample_token(logits[b], temperature, top_k, top_p, philox_uniform(seed, step, b))
+                 for b in range(logits.shape[0])]
+        nxt = torch.tensor([p[0] for p in picks], dtype=torch.int64)
+        margins.append([p[1] for p in picks])
+        out.append(nxt)
+        if step + 1 < max_new_tokens:
+            logits = llama_forward(emb[nxt][:, None, :], sd, g, cache)
+    ids_out = torch.stack(out, dim=1)
+    return (ids_out, trace, margins) if return_logits else ids_out

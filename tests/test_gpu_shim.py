@@ -89,5 +89,7 @@ def test_reference_error_behaviour():
     im2, sg2 = synth.make_pixels(g, 2, 1), synth.make_pixels(g, 2, 2)
     with pytest.raises(NameError):  # ragged batch
         m2.generate(torch.tensor([[1, I, S, 7], [1, 5, 6, 7]]), images=im2, segs=sg2, depths=im2, max_new_tokens=2)
+    with pytest.raises(ValueError):  # HF: `temperature` has to be a strictly positive float
+        m2.generate(torch.tensor([[1, I, S, 7]]), images=images, segs=segs, do_sample=True, temperature=0.0, max_new_tokens=2)
     with pytest.raises(NotImplementedError):
-        m2.generate(torch.tensor([[1, I, S, 7]]), images=images, segs=segs, do_sample=True, temperature=0.2, max_new_tokens=2)
+        m2.generate(torch.tensor([[1, I, S, 7]]), images=images, segs=segs, num_beams=2, max_new_tokens=2)

@@ -44,6 +44,9 @@ _i32 = C.c_int32
 _i64 = C.c_int64
 _f = C.c_float
 
+# int cb(void* user, int32 step, const int32* ids_host, int32 B)  (vcb_token_callback)
+TOKEN_CALLBACK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32)
+
 # name -> (restype, argtypes): every symbol declared in include/vcoder_b200.h
 SIGNATURES = {
     "vcb_version": (C.c_char_p, []),
@@ -64,6 +67,10 @@ SIGNATURES = {
     "vcb_prefill": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
     "vcb_decode": (C.c_int, [_p, _i32, _p, _p, _p]),
     "vcb_generate": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _i32, _p, _p]),
+    "vcb_set_sampling": (C.c_int, [_p, _i32, _f, _i32, _f, C.c_uint64, _p]),
+    "vcb_decode_stream": (C.c_int, [_p, _i32, _i32, TOKEN_CALLBACK, _p, _p, _p]),
+    "vcb_op_sample_f16": (C.c_int, [_p, _i32, _i32, _f, _i32, _f, C.c_uint64, _i32, _p, _p, _p]),
+    "vcb_philox_uniform": (C.c_float, [C.c_uint64, C.c_uint32, C.c_uint32]),
     "vcb_reset": (C.c_int, [_p]),
     "vcb_launch_count": (C.c_uint64, []),
     "vcb_profile_enable": (C.c_int, [_i32]),

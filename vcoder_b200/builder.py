@@ -93,4 +93,12 @@ def load_pretrained_model(model_path, model_base, model_name, load_8bit=False, l
     dev_index = torch.device(device).index or 0
     model = build_model(model_name, g, sd, max_batch=max_batch, max_seq_len=max(context_len, 2048), device=dev_index,
                         image_processor=image_processor)
+    # generation defaults HF would read: generation_config.json, else the model config's eos/pad ids
+    gen = {}
+    gpath = os.path.join(model_path, "generation_config.json")
+    if os.path.exists(gpath):
+        gen = json.load(open(gpath))
+    model.generation_config.eos_token_id = gen.get("eos_token_id", cfg.get("eos_token_id"))
+    model.generation_config.pad_token_id = gen.get("pad_token_id", cfg.get("pad_token_id"))
+    model.generation_config.top_k = gen.get("top_k", 50)
     return tokenizer, model, image_processor, seg_image_processor, depth_image_processor, context_len

@@ -217,6 +217,41 @@ int vcb_generate(vcb_handle h, const int64_t* ids, int32_t B, int32_t T, const v
   return kOk;
 }
 
+int vcb_set_sampling(vcb_handle h, int32_t do_sample, float temperature, int32_t top_k, float top_p, uint64_t seed,
+                     void* stream) {
+  VCB_CHECK(h != nullptr, kErrInvalid, "null handle");
+  StreamGuard sg(h->e, ST(stream));
+  return engine_set_sampling(h->e, do_sample, temperature, top_k, top_p, seed, sg.st);
+}
+
+int vcb_decode_stream(vcb_handle h, int32_t max_steps, int32_t lookahead, vcb_token_callback cb, void* user,
+                      int32_t* n_accepted, void* stream) {
+  VCB_CHECK(h != nullptr, kErrInvalid, "null handle");
+  StreamGuard sg(h->e, ST(stream));
+  return engine_decode_stream(h->e, max_steps, lookahead, cb, user, n_accepted, sg.st);
+}
+
+int vcb_op_sample_f16(const vcb_half* logits, int32_t B, int32_t V, float temperature, int32_t top_k, float top_p,
+                      uint64_t seed, int32_t step, int32_t* next_ids, int32_t* kept, void* stream) {
+  VCB_TRY(require_device());
+  VCB_CHECK(logits != nullptr && next_ids != nullptr && B >= 1, kErrInvalid, "vcb_op_sample_f16: bad arguments");
+  VCB_CHECK(temperature > 0.f && top_k >= 0 && top_p >= 0.f && top_p <= 1.f, kErrInvalid,
+            "vcb_op_sample_f16: temperature > 0, top_k >= 0, 0 <= top_p <= 1");
+  unsigned char blk[32] = {0};
+  pack_sample_params(temperature, top_k, top_p, seed, blk);
+  void* prm = nullptr;
+  VCB_CUDA(cudaMallocAsync(&prm, 32, ST(stream)));
+  VCB_CUDA(cudaMemcpyAsync(prm, blk, 32, cudaMemcpyHostToDevice, ST(stream)));
+  const int rc = sample_rows(H(logits), B, V, prm, nullptr, step, next_ids, nullptr, 0, kept, ST(stream));
+  cudaFreeAsync(prm, ST(stream));
+  VCB_CUDA(cudaStreamSynchronize(ST(stream)));  // blk is a stack buffer
+  return rc;
+}
+
+float vcb_philox_uniform(uint64_t seed, uint32_t step, uint32_t row) {
+  return static_cast<float>(philox_first_host(seed, step, row) >> 8) * (1.0f / 16777216.0f);
+}
+
 int vcb_reset(vcb_handle h) {
   VCB_CHECK(h != nullptr, kErrInvalid, "null handle");
   return engine_reset(h->e);

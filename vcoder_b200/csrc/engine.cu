@@ -7,6 +7,7 @@
 #include "engine.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 
@@ -66,6 +67,8 @@ Engine::~Engine() {
   if (own_stream) cudaStreamDestroy(own_stream);
   if (ev_in) cudaEventDestroy(ev_in);
   if (ev_out) cudaEventDestroy(ev_out);
+  for (cudaEvent_t ev : stream_ev) if (ev) cudaEventDestroy(ev);
+  if (stream_host) cudaFreeHost(stream_host);
   for (void* p : allocs) cudaFree(p);
   if (plan_host) cudaFreeHost(plan_host);
   if (bt_host) cudaFreeHost(bt_host);
@@ -167,11 +170,13 @@ int engine_create(const vcb_config* c, int device, Engine** out) {
   if (rc == kOk) rc = dev_alloc(e, &e->block_table, static_cast<size_t>(B) * e->max_pages_per_seq * 4);
   if (rc == kOk) rc = dev_alloc(e, &e->rope, static_cast<size_t>(c->max_seq_len) * 64 * sizeof(float2));
   if (rc == kOk) rc = dev_alloc(e, &e->counters, 16);
+  if (rc == kOk) rc = dev_alloc(e, &e->sample_params, 32);
 #undef ALLOC
   if (rc != kOk) { delete e; return rc; }
   if (cudaMallocHost(&e->plan_host, e->max_rows * 4) != cudaSuccess ||
       cudaMallocHost(&e->bt_host, static_cast<size_t>(B) * e->max_pages_per_seq * 4) != cudaSuccess ||
-      cudaMallocHost(&e->depth_host, B * 4) != cudaSuccess) {
+      cudaMallocHost(&e->depth_host, B * 4) != cudaSuccess ||
+      cudaMallocHost(&e->stream_host, static_cast<size_t>(Engine::kStreamRing) * B * 4) != cudaSuccess) {
     delete e;
     set_thread_error("cudaMallocHost failed");
     return kErrNoMem;
@@ -186,6 +191,13 @@ int engine_create(const vcb_config* c, int device, Engine** out) {
     }
     cudaMemset(e->patch_w.p, 0, e->patch_w.bytes);
     cudaMemset(e->counters.p, 0, 16);
+    for (cudaEvent_t& ev : e->stream_ev) {
+      if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+        delete e;
+        set_thread_error("event creation failed");
+        return kErrCuda;
+      }
+    }
   }
   *out = e;
   return kOk;
@@ -499,6 +511,16 @@ int splice_plan_host(int variant, const int64_t* ids, int B, int T, int n_patche
 // ------------------------------------------------------------------------------------------------------------
 namespace {
 
+// next token of every sequence from e->logits: greedy argmax, or HF sample() when vcb_set_sampling enabled it
+int select_next(Engine* e, int B, const int32_t* step_dev, cudaStream_t st) {
+  const vcb_config& c = e->cfg;
+  if (e->sampling)
+    return sample_rows(e->logits.as<__half>(), B, c.llm_vocab, e->sample_params.p, step_dev, 0,
+                       e->next_ids.as<int32_t>(), e->trace.as<int32_t>(), c.max_seq_len, nullptr, st);
+  return argmax_rows(e->logits.as<__half>(), B, c.llm_vocab, e->next_ids.as<int32_t>(), e->trace.as<int32_t>(),
+                     c.max_seq_len, step_dev, st);
+}
+
 __global__ void depth_sum_kernel(const __half* px, long per_image, float* sums) {
   const int b = blockIdx.y;
   const __half* p = px + b * per_image;
@@ -646,8 +668,7 @@ int engine_prefill(Engine* e, const int64_t* ids, int B, int T, const void* imag
   int32_t* counters = e->counters.as<int32_t>();
   const int32_t init[3] = {Tp, 0, Tp + 1};
   VCB_CUDA(cudaMemcpyAsync(counters, init, 12, cudaMemcpyHostToDevice, st));
-  VCB_TRY(argmax_rows(e->logits.as<__half>(), B, V, e->next_ids.as<int32_t>(), e->trace.as<int32_t>(), c.max_seq_len,
-                      counters + 1, st));
+  VCB_TRY(select_next(e, B, counters + 1, st));
   const int32_t after[3] = {Tp, 1, Tp + 1};
   VCB_CUDA(cudaMemcpyAsync(counters, after, 12, cudaMemcpyHostToDevice, st));
   if (last_logits_out) VCB_TRY(copy_any(last_logits_out, e->logits.p, static_cast<size_t>(B) * V * 2, st));
@@ -733,9 +754,39 @@ int decode_step_launch(Engine* e, int max_ctx, cudaStream_t st) {
     s.X = fuse_norm ? x : xn; s.ldx = H; s.W = e->lm_head.as<__half>(); s.Y = e->logits.as<__half>(); s.ldy = V; s.B = B; s.N = V; s.K = H;
     VCB_TRY(skinny_gemm(s, st));
   }
-  VCB_TRY(argmax_rows(e->logits.as<__half>(), B, V, e->next_ids.as<int32_t>(), e->trace.as<int32_t>(), c.max_seq_len,
-                      counters + 1, st));
+  VCB_TRY(select_next(e, B, counters + 1, st));
   VCB_TRY(advance_counters(counters, st));
+  return kOk;
+}
+
+}  // namespace
+
+namespace {
+
+// Makes e->graph a replayable capture of one decode step for (batch, splits, greedy|sampling).  Building it runs ONE
+// eager step first (sets per-kernel attributes outside capture and validates the launch sequence): *ran_eager = 1 then.
+int ensure_graph(Engine* e, int max_ctx, cudaStream_t st, int* ran_eager) {
+  const int B = e->batch, splits = attn_decode_splits(max_ctx), mode = e->sampling ? 1 : 0;
+  *ran_eager = 0;
+  if (e->graph != nullptr && e->graph_batch == B && e->graph_splits == splits && e->graph_sampling == mode) return kOk;
+  VCB_TRY(decode_step_launch(e, max_ctx, st));
+  *ran_eager = 1;
+  if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
+  cudaGraph_t g = nullptr;
+  const uint64_t c0 = launch_count();
+  VCB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  const int rc = decode_step_launch(e, max_ctx, st);
+  cudaError_t ce = cudaStreamEndCapture(st, &g);
+  e->graph_kernels = static_cast<int>(launch_count() - c0);
+  launch_count_add(-static_cast<int64_t>(e->graph_kernels));  // captured, not executed
+  if (rc != kOk) { if (g) cudaGraphDestroy(g); return rc; }
+  VCB_CUDA(ce);
+  ce = cudaGraphInstantiate(&e->graph, g, 0);
+  cudaGraphDestroy(g);
+  VCB_CUDA(ce);
+  e->graph_batch = B;
+  e->graph_splits = splits;
+  e->graph_sampling = mode;
   return kOk;
 }
 
@@ -751,30 +802,10 @@ int engine_decode(Engine* e, int n_steps, void* out_ids, void* logits_trace, cud
   VCB_CHECK(e->cache_len + n_steps <= c.max_seq_len, kErrNoMem, "vcb_decode: would exceed max_seq_len");
   VCB_TRY(ensure_pages(e, B, e->cache_len + n_steps, st));
   const int max_ctx = e->cache_len + n_steps;
-  const int splits = attn_decode_splits(max_ctx);
   int done = 0;
   const bool use_graph = logits_trace == nullptr && n_steps >= 3 && !prof_enabled();
   if (use_graph) {
-    if (e->graph == nullptr || e->graph_batch != B || e->graph_splits != splits) {
-      // one eager step first: sets per-kernel attributes outside capture and validates the launch sequence
-      VCB_TRY(decode_step_launch(e, max_ctx, st));
-      ++done;
-      if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
-      cudaGraph_t g = nullptr;
-      const uint64_t c0 = launch_count();
-      VCB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-      const int rc = decode_step_launch(e, max_ctx, st);
-      cudaError_t ce = cudaStreamEndCapture(st, &g);
-      e->graph_kernels = static_cast<int>(launch_count() - c0);
-      launch_count_add(-static_cast<int64_t>(e->graph_kernels));  // captured, not executed
-      if (rc != kOk) { if (g) cudaGraphDestroy(g); return rc; }
-      VCB_CUDA(ce);
-      ce = cudaGraphInstantiate(&e->graph, g, 0);
-      cudaGraphDestroy(g);
-      VCB_CUDA(ce);
-      e->graph_batch = B;
-      e->graph_splits = splits;
-    }
+    VCB_TRY(ensure_graph(e, max_ctx, st, &done));
     for (; done < n_steps; ++done) {
       VCB_CUDA(cudaGraphLaunch(e->graph, st));
       launch_count_add(e->graph_kernels);
@@ -794,6 +825,108 @@ int engine_decode(Engine* e, int n_steps, void* out_ids, void* logits_trace, cud
                                static_cast<size_t>(c.max_seq_len) * 4, static_cast<size_t>(n_steps) * 4, B,
                                cudaMemcpyDefault, st));
   }
+  return kOk;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// f1: sampling parameters and the streamed decode loop (serve/cli.py:117-132, serve/chat.py:131-159)
+// ------------------------------------------------------------------------------------------------------------
+int engine_set_sampling(Engine* e, int do_sample, float temperature, int top_k, float top_p, uint64_t seed,
+                        cudaStream_t st) {
+  VCB_CUDA(cudaSetDevice(e->device));
+  if (!do_sample) {
+    e->sampling = false;
+    return kOk;
+  }
+  // the same argument checks HF's warpers make (logits_process.py: Temperature / TopK / TopP __init__)
+  VCB_CHECK(temperature > 0.f && std::isfinite(temperature), kErrInvalid,
+            "`temperature` has to be a strictly positive float");
+  VCB_CHECK(top_k >= 0, kErrInvalid, "`top_k` has to be a non-negative integer (0 disables the filter)");
+  VCB_CHECK(top_p >= 0.f && top_p <= 1.f, kErrInvalid, "`top_p` has to be a float >= 0 and <= 1");
+  VCB_CHECK(e->cfg.llm_vocab <= 32768, kErrInvalid, "sampling: vocabulary larger than 32768 is not supported");
+  unsigned char blk[32] = {0};
+  pack_sample_params(temperature, top_k, top_p, seed, blk);
+  // ordered on the stream: a step already queued keeps the parameters it was launched with
+  VCB_CUDA(cudaMemcpyAsync(e->sample_params.p, blk, 32, cudaMemcpyHostToDevice, st));
+  VCB_CUDA(cudaStreamSynchronize(st));  // blk is a stack buffer
+  e->sampling = true;
+  return kOk;
+}
+
+int engine_decode_stream(Engine* e, int max_steps, int lookahead, engine_token_cb cb, void* user, int* n_accepted,
+                         cudaStream_t st) {
+  const vcb_config& c = e->cfg;
+  VCB_CHECK(e->prefilled, kErrState, "vcb_decode_stream called before vcb_prefill");
+  VCB_CHECK(max_steps >= 0 && cb != nullptr, kErrInvalid, "vcb_decode_stream: bad arguments");
+  VCB_CUDA(cudaSetDevice(e->device));
+  if (n_accepted) *n_accepted = 0;
+  if (max_steps == 0) return kOk;
+  const int B = e->batch;
+  const int R = Engine::kStreamRing;
+  lookahead = std::max(1, std::min(lookahead, R));
+  VCB_CHECK(e->cache_len + max_steps <= c.max_seq_len, kErrNoMem, "vcb_decode_stream: would exceed max_seq_len");
+  VCB_TRY(ensure_pages(e, B, e->cache_len + max_steps, st));
+  const int max_ctx = e->cache_len + max_steps;
+  const int first_token = e->steps_done;
+  const bool use_graph = !prof_enabled();
+  int issued = 0, consumed = 0, accepted = 0;
+  bool stop = false;
+  int rc = kOk;
+  auto issue_one = [&]() -> int {
+    int ran = 0;
+    if (use_graph) VCB_TRY(ensure_graph(e, max_ctx, st, &ran));
+    if (!ran) {
+      if (use_graph) {
+        VCB_CUDA(cudaGraphLaunch(e->graph, st));
+        launch_count_add(e->graph_kernels);
+      } else {
+        VCB_TRY(decode_step_launch(e, max_ctx, st));
+      }
+    }
+    const int slot = issued % R;
+    VCB_CUDA(cudaMemcpy2DAsync(e->stream_host + static_cast<size_t>(slot) * B, 4,
+                               e->trace.as<int32_t>() + first_token + issued, static_cast<size_t>(c.max_seq_len) * 4, 4,
+                               B, cudaMemcpyDeviceToHost, st));
+    VCB_CUDA(cudaEventRecord(e->stream_ev[slot], st));
+    ++issued;
+    return kOk;
+  };
+  while (!stop && consumed < max_steps) {
+    while (issued < max_steps && issued - consumed < lookahead) {
+      rc = issue_one();
+      if (rc != kOk) break;
+    }
+    if (rc != kOk) break;
+    const int slot = consumed % R;
+    if (cudaEventSynchronize(e->stream_ev[slot]) != cudaSuccess) {
+      set_thread_error("cudaEventSynchronize failed in vcb_decode_stream");
+      rc = kErrCuda;
+      break;
+    }
+    stop = cb(user, consumed, e->stream_host + static_cast<size_t>(slot) * B, B) != 0;
+    ++consumed;
+    accepted = consumed;
+  }
+  // steps queued past the accepted one are discarded: wait for them, then roll the device state back
+  cudaError_t se = cudaStreamSynchronize(st);
+  if (rc == kOk && se != cudaSuccess) {
+    set_thread_error(std::string("vcb_decode_stream: ") + cudaGetErrorString(se));
+    rc = kErrCuda;
+  }
+  if (rc != kOk) {
+    e->prefilled = false;  // device counters are ahead of the host mirror: force a new prefill
+    return rc;
+  }
+  e->cache_len += accepted;
+  e->steps_done += accepted;
+  if (issued > accepted) {
+    const int32_t ctr[3] = {e->cache_len, e->steps_done, e->cache_len + 1};
+    VCB_CUDA(cudaMemcpyAsync(e->counters.p, ctr, 12, cudaMemcpyHostToDevice, st));
+    VCB_CUDA(cudaMemcpy2DAsync(e->next_ids.p, 4, e->trace.as<int32_t>() + e->steps_done - 1,
+                               static_cast<size_t>(c.max_seq_len) * 4, 4, B, cudaMemcpyDeviceToDevice, st));
+    VCB_CUDA(cudaStreamSynchronize(st));  // ctr is a stack buffer
+  }
+  if (n_accepted) *n_accepted = accepted;
   return kOk;
 }
 

@@ -76,7 +76,13 @@ struct Engine {
   cudaGraphExec_t graph = nullptr;
   cudaStream_t own_stream = nullptr;   // used when the caller hands us the legacy default stream
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
-  int graph_batch = 0, graph_splits = 0, graph_kernels = 0;
+  int graph_batch = 0, graph_splits = 0, graph_kernels = 0, graph_sampling = 0;
+  // f1: sampling + per-token streaming
+  DevBuf sample_params;      // SampleDeviceParams (sample.cu), read by the sampling kernel inside the captured graph
+  bool sampling = false;     // do_sample: the next-token kernel is sample_rows instead of argmax_rows
+  static constexpr int kStreamRing = 16;
+  cudaEvent_t stream_ev[kStreamRing] = {};
+  int32_t* stream_host = nullptr;  // pinned [kStreamRing][max_batch]
 
   ~Engine();
 };
@@ -92,6 +98,15 @@ int engine_prefill(Engine* e, const int64_t* ids_host, int B, int T, const void*
                    cudaStream_t st);
 int engine_decode(Engine* e, int n_steps, void* out_ids, void* logits_trace, cudaStream_t st);
 int engine_reset(Engine* e);
+// do_sample / temperature / top_k / top_p / seed of the following prefill + decode calls (HF GenerationMixin.sample)
+int engine_set_sampling(Engine* e, int do_sample, float temperature, int top_k, float top_p, uint64_t seed,
+                        cudaStream_t st);
+// Decode with the host in the loop: up to `lookahead` steps stay queued on the GPU while cb() sees the tokens of step i
+// (TextStreamer.put / KeywordsStoppingCriteria / eos checks of serve/cli.py:117-132).  cb != 0 stops: the steps already
+// queued are discarded and the device counters are rolled back, so a later decode continues after the accepted token.
+typedef int (*engine_token_cb)(void* user, int step, const int32_t* ids, int B);
+int engine_decode_stream(Engine* e, int max_steps, int lookahead, engine_token_cb cb, void* user, int* n_accepted,
+                         cudaStream_t st);
 int copy_any(void* dst, const void* src, size_t bytes, cudaStream_t st);
 
 // Work always runs on a capturable (non-legacy) stream.  When the caller passes NULL / the legacy default stream,

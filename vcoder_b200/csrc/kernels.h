@@ -90,6 +90,12 @@ int embed_gather(const int32_t* ids, const __half* embed, __half* out, int B, in
 // first-index argmax over fp16 logits [B,V]; writes next[b] and (optionally) trace[b*trace_stride + *step]
 int argmax_rows(const __half* logits, int B, int V, int32_t* next, int32_t* trace, int trace_stride,
                 const int32_t* step_dev, cudaStream_t s);
+// do_sample=True: temperature -> top-k (ties kept) -> top-p -> inverse-CDF draw at u = Philox(seed; step, row) on the
+// bitonic-sorted row (sample.cu).  params_dev: 20-byte block written by pack_sample_params; step = *step_dev or step_host.
+int sample_rows(const __half* logits, int B, int V, const void* params_dev, const int32_t* step_dev, int step_host,
+                int32_t* next, int32_t* trace, int trace_stride, int32_t* kept_out, cudaStream_t s);
+void pack_sample_params(float temperature, int top_k, float top_p, uint64_t seed, void* out20);
+uint32_t philox_first_host(uint64_t seed, uint32_t step, uint32_t row);
 int compact_patches(const __half* hidden, __half* out, int B, int tokens, int D, cudaStream_t s);
 int advance_counters(int32_t* counters, cudaStream_t s);
 void build_rope_table(float2* host_table, int max_pos, int head_dim, float theta);

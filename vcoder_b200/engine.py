@@ -144,6 +144,47 @@ class Engine:
                                              max_new_tokens, _lib.ptr(out), _stream_ptr()))
         return out
 
+    # ---- f1: sampling + per-token streaming --------------------------------------------------------------
+    def set_sampling(self, do_sample: bool, temperature: float = 1.0, top_k: int = 50, top_p: float = 1.0,
+                     seed: int = 0) -> None:
+        """do_sample / temperature / top_k / top_p of the following prefill / decode / generate calls (HF sample())."""
+        with self.lock:
+            _lib.check(self.lib.vcb_set_sampling(self.h, int(bool(do_sample)), float(temperature), int(top_k),
+                                                 float(top_p), int(seed) & 0xFFFFFFFFFFFFFFFF, _stream_ptr()))
+
+    def decode_stream(self, max_steps: int, on_token, lookahead: int = 4) -> int:
+        """Up to `max_steps` decode steps; `on_token(step, ids: list[int]) -> bool` runs on the host for every token
+        while the GPU already works on the next `lookahead` steps; returning True stops after that token (the KV
+        length and RNG step are rolled back to it).  Returns the number of tokens delivered."""
+        err = []
+
+        def _cb(_user, step, ids_p, B):
+            try:
+                return 1 if on_token(int(step), [int(ids_p[i]) for i in range(B)]) else 0
+            except BaseException as ex:  # never unwind through the C frames
+                err.append(ex)
+                return 1
+
+        cb = _lib.TOKEN_CALLBACK(_cb)
+        n = C.c_int32(0)
+        with self.lock:
+            rc = self.lib.vcb_decode_stream(self.h, int(max_steps), int(lookahead), cb, None, C.byref(n), _stream_ptr())
+        if err:
+            raise err[0]
+        _lib.check(rc)
+        return n.value
+
+    def sample_op(self, logits: torch.Tensor, temperature: float, top_k: int, top_p: float, seed: int, step: int = 0):
+        """Operator-level entry (parity tests): logits [B,V] fp16 on the device -> (next_ids [B], kept [B]) int32."""
+        lg = logits.to(self.tdev, torch.float16).contiguous()
+        B, V = lg.shape
+        nxt = torch.empty(B, dtype=torch.int32, device=self.tdev)
+        kept = torch.empty(B, dtype=torch.int32, device=self.tdev)
+        _lib.check(self.lib.vcb_op_sample_f16(_lib.ptr(lg), B, V, float(temperature), int(top_k), float(top_p),
+                                              int(seed) & 0xFFFFFFFFFFFFFFFF, int(step), _lib.ptr(nxt), _lib.ptr(kept),
+                                              _stream_ptr()))
+        return nxt, kept
+
     def reset(self):
         _lib.check(self.lib.vcb_reset(self.h))
 

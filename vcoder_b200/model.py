@@ -86,6 +86,10 @@ class _VCoderBase:
             rms_norm_eps=g.llm_rms_eps, max_position_embeddings=max_seq_len, mm_vision_select_layer=g.vit_select_layer,
             mm_vision_select_feature="patch", mm_projector_type="mlp2x_gelu", seg_mm_projector_type="mlp2x_gelu",
             mm_hidden_size=g.vit_hidden, use_cache=True, pad_token_id=0, bos_token_id=1, eos_token_id=2)
+        # GenerationConfig defaults the callers rely on implicitly: top_k = 50 applies whenever do_sample=True;
+        # eos/pad come from the checkpoint (builder.load_pretrained_model fills them in), None = never stop early
+        self.generation_config = types.SimpleNamespace(eos_token_id=None, pad_token_id=None, top_k=50)
+        self.stream_lookahead = 4  # decode steps kept queued on the GPU while Python handles a token
         if state_dict is not None:
             self.load_state_dict(state_dict)
 
@@ -130,51 +134,86 @@ class _VCoderBase:
     def encode_seg_images(self, seg_images):
         return self._eng.encode(1, seg_images)
 
-    # ---- a5/a6: generate -------------------------------------------------------------------------------------------
+    # ---- a5/a6 + f1: generate ----------------------------------------------------------------------------------
     @torch.no_grad()
     def generate(self, input_ids=None, images=None, segs=None, depths=None, do_sample: bool = False,
-                 temperature: float = 1.0, top_p: Optional[float] = None, num_beams: int = 1,
-                 max_new_tokens: int = 20, use_cache: bool = True, streamer=None, stopping_criteria=None,
-                 attention_mask=None, eos_token_id=None, pad_token_id=None, **kwargs):
-        """Greedy `GenerationMixin.generate` semantics: returns cat([input_ids, new_ids]) on
-        input_ids' device; callers slice `[:, input_ids.shape[1]:]` (eval/model_depth_loader.py:170-174)."""
+                 temperature: float = 1.0, top_p: Optional[float] = None, top_k: Optional[int] = None,
+                 num_beams: int = 1, max_new_tokens: int = 20, use_cache: bool = True, streamer=None,
+                 stopping_criteria=None, attention_mask=None, eos_token_id=None, pad_token_id=None, seed=None,
+                 inputs=None, **kwargs):
+        """`GenerationMixin.generate` semantics for the two modes the callers use: greedy
+        (eval/model_*_loader.py with --temperature 0) and do_sample=True with temperature / top_p (serve/cli.py:121-132,
+        serve/chat.py:141-151; top_k = 50 is HF's GenerationConfig default).  Returns cat([input_ids, new_ids]) on
+        input_ids' device; callers slice `[:, input_ids.shape[1]:]` (eval/model_depth_loader.py:170-174).
+
+        Sampling runs on the device (csrc/sample.cu).  `seed` fixes the Philox stream; None draws one from torch's
+        global generator, so `torch.manual_seed` makes a run reproducible as it does for the reference."""
+        if input_ids is None:
+            input_ids = inputs  # serve/chat.py:141 passes `inputs=`
         if input_ids is None:
             raise ValueError("generate() needs input_ids")
-        if do_sample and temperature not in (0, 0.0):
-            raise NotImplementedError("sampling (do_sample=True) is SURVEY §8 row f1 ('next'); greedy only for now")
         if num_beams != 1:
             raise NotImplementedError("beam search is not on the reference's hot path (num_beams=1 everywhere)")
         if attention_mask is not None and not bool(torch.as_tensor(attention_mask).bool().all()):
             raise NotImplementedError("padded prompts: the reference itself mis-aligns the mask after the splice")
         if self.variant == synth.VARIANT_VCODER and depths is not None:
             raise TypeError("VCoderLlavaLlamaForCausalLM.generate() got an unexpected keyword argument 'depths'")
+        gc = self.generation_config
+        if eos_token_id is None:
+            eos_token_id = gc.eos_token_id
+        if pad_token_id is None:
+            pad_token_id = gc.pad_token_id if gc.pad_token_id is not None else eos_token_id
+        if do_sample:
+            # the argument checks of HF's warpers (logits_process.py), same exception type
+            if not (isinstance(temperature, (int, float)) and temperature > 0):
+                raise ValueError(f"`temperature` (={temperature}) has to be a strictly positive float")
+            tp = 1.0 if top_p is None else float(top_p)
+            if not 0.0 <= tp <= 1.0:
+                raise ValueError(f"`top_p` has to be a float > 0 and < 1, but is {top_p}")
+            tk = gc.top_k if top_k is None else int(top_k)
+            if tk < 0:
+                raise ValueError(f"`top_k` has to be a non-negative integer, but is {top_k}")
+            if seed is None:
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            self._eng.set_sampling(True, float(temperature), tk, tp, seed)
+        else:
+            self._eng.set_sampling(False)
         dev = input_ids.device
         B = input_ids.shape[0]
-        interactive = streamer is not None or stopping_criteria is not None or eos_token_id is not None
+        interactive = streamer is not None or bool(stopping_criteria) or eos_token_id is not None
         try:
             if not interactive:
                 new = self._eng.generate(input_ids, images, segs, depths, max_new_tokens=max_new_tokens)
                 return torch.cat([input_ids.to(dev), new.to(dev)], dim=1)
-            # token-by-token path: streamer / KeywordsStoppingCriteria (mm_utils.py:128-151) / eos need host ids
-            pre = self._eng.prefill(input_ids, images, segs, depths)
-            seq = torch.cat([input_ids.cpu(), pre["next_ids"].cpu().long()[:, None]], dim=1)
+            # token-by-token: TextStreamer / KeywordsStoppingCriteria (mm_utils.py:128-151) / eos need host ids.  The
+            # GPU keeps `lookahead` steps queued while Python looks at a token (vcb_decode_stream).
+            eos = None if eos_token_id is None else set(eos_token_id if isinstance(eos_token_id, (list, tuple)) else [eos_token_id])
+            seq = input_ids.cpu().long()
+            unfinished = torch.ones(B, dtype=torch.bool)
             if streamer is not None:
-                streamer.put(input_ids.cpu())
-                streamer.put(seq[:, -1])
-            finished = torch.zeros(B, dtype=torch.bool)
-            for _ in range(max_new_tokens - 1):
-                if eos_token_id is not None:
-                    finished |= seq[:, -1] == eos_token_id
-                if bool(finished.all()):
-                    break
-                if stopping_criteria is not None and all(sc(seq, None) for sc in stopping_criteria):
-                    break
-                nxt = self._eng.decode(1).cpu().long()
-                if eos_token_id is not None and pad_token_id is not None:
-                    nxt[finished] = pad_token_id
-                seq = torch.cat([seq, nxt], dim=1)
+                streamer.put(seq)
+
+            def on_token(_step, ids):
+                # the body of HF's sample()/greedy_search() loop after the token is chosen
+                nonlocal seq, unfinished
+                nxt = torch.tensor(ids, dtype=torch.long)
+                if eos is not None:
+                    nxt = torch.where(unfinished, nxt, torch.full_like(nxt, pad_token_id))
+                seq = torch.cat([seq, nxt[:, None]], dim=1)
                 if streamer is not None:
-                    streamer.put(nxt[:, 0])
+                    streamer.put(nxt)
+                done = False
+                if eos is not None:
+                    unfinished = unfinished & torch.tensor([int(t) not in eos for t in nxt.tolist()])
+                    done = not bool(unfinished.any())
+                if stopping_criteria and all(bool(sc(seq, None)) for sc in stopping_criteria):
+                    done = True
+                return done
+
+            pre = self._eng.prefill(input_ids, images, segs, depths)
+            stop = on_token(0, pre["next_ids"].cpu().tolist())
+            if not stop and max_new_tokens > 1:
+                self._eng.decode_stream(max_new_tokens - 1, on_token, lookahead=self.stream_lookahead)
             if streamer is not None:
                 streamer.end()
             return seq.to(dev)
