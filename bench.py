@@ -179,7 +179,7 @@ def run_reference(args):
     vals = []
     last = None
     for i in range(args.warmup + args.steps):
-        last = cpu_sample_tokens_per_s(args.batch, args.new_tokens, repeats=1)
+        last = cpu_sample_tokens_per_s(args.batch, args.new_tokens, repeats=3)
         if i >= args.warmup:
             vals.append(last["value"])
     v = sum(vals) / len(vals)
@@ -298,7 +298,7 @@ def run_b200(args):
     e2e_value = tokens / (ms_e2e / 1e3)
 
     # ---- live per-kernel timing of one more step (CUDA events around every launch, graph disabled)
-    roofline, breakdown, phases = None, None, None
+    roofline, breakdown, phases, vit = None, None, None, None
     if rank == 0:
         import ctypes as C
         peaks = load_peaks()
@@ -331,7 +331,15 @@ def run_b200(args):
         step_bytes = 2 * (L * (3 * H * H + H * H + 2 * F * H + H * F) + V * H)
         sk = breakdown["skinny_gemm"]
         total_bytes = step_bytes * (N - 1) + 2 * V * H  # + the prefill's last-position lm_head
-        ach = total_bytes / (sk["ms"] / 1e3) / 1e9 if sk["ms"] else None
+        ach_events = total_bytes / (sk["ms"] / 1e3) / 1e9 if sk["ms"] else None
+        # average launch duration, live: the step's 4L+1 weight-streaming launches on the bound weights, back to back
+        # with PDL as in the decode graph, between two CUDA events on the launching stream (13.2 GB per round >> L2)
+        rounds = 10
+        ms_ws, n_ws = C.c_float(0), C.c_int32(0)
+        _lib.check(lib.vcb_bench_weight_stream(eng.h, B, rounds, C.byref(ms_ws), C.byref(n_ws), C.c_void_p(stream.cuda_stream)))
+        avg_launch_us = ms_ws.value * 1e3 / max(1, n_ws.value)
+        bytes_per_launch = step_bytes * rounds / max(1, n_ws.value)
+        ach = bytes_per_launch / (avg_launch_us * 1e-6) / 1e9 if avg_launch_us else None
         traffic = None
         tp = os.path.join(ROOT, "profiles", "skinny_traffic.json")
         if os.path.exists(tp):
@@ -339,11 +347,35 @@ def run_b200(args):
         roofline = {"kernel": "skinny_tma_kernel (TMA-fed decode weight streaming: qkv/o/gate-up/down/lm_head)", "bound": "hbm",
                     "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": (ach / peaks["hbm_gbs"]) if ach else None,
                     "traffic": traffic, "peak_source": peaks["source"],
-                    "bytes_per_launch_avg": total_bytes / max(1, sk["launches"]), "launches": sk["launches"],
-                    "note": "CUDA events bracket each launch (~2 us event overhead included)"}
+                    "bytes_per_launch_avg": bytes_per_launch, "avg_launch_us": avg_launch_us, "launches": n_ws.value,
+                    "how": f"{rounds} rounds of the decode step's {n_ws.value // rounds} weight-streaming launches (real weights, "
+                           "PDL, one stream) between two CUDA events; algorithmic bytes = weight bytes, read once",
+                    "achieved_with_per_launch_events": ach_events,
+                    "note": "achieved_with_per_launch_events = same bytes / sum of per-launch event pairs inside one full "
+                            "job (graph off, ~2 us event overhead per launch, no PDL overlap): a lower bound"}
+        # secondary: the kernel the north star names (CLIP self-attention) and the three-tower throughput
+        n_img_layers = 3 * B * (g.vit_layers - 1)
+        av = breakdown["attn_vit"]
+        attn_us = av["ms"] * 1e3 / n_img_layers if av["ms"] else None
+        attn_bytes = 4 * (g.n_patches + 1) * g.vit_hidden * 2
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        px_all = torch.cat(dev_px, dim=0)
+        eng.tower_forward(px_all)
+        ev[0].record(stream)
+        for _ in range(3):
+            eng.tower_forward(px_all)
+        ev[1].record(stream)
+        torch.cuda.synchronize()
+        tower_ms = ev[0].elapsed_time(ev[1]) / 3
+        vit = {"images": 3 * B, "tower_ms": round(tower_ms, 3), "images_per_s": round(3 * B / (tower_ms / 1e3), 1),
+               "tower_tflops": round(3 * B * 366e9 / (tower_ms / 1e3) / 1e12, 1),
+               "attn_us_per_image_layer": round(attn_us, 3) if attn_us else None,
+               "attn_hbm_frac": round(attn_bytes / (attn_us * 1e-6) / 1e9 / peaks["hbm_gbs"], 4) if attn_us else None,
+               "attn_tflops": round(4 * (g.n_patches + 1) ** 2 * g.vit_hidden / (attn_us * 1e-6) / 1e12, 1) if attn_us else None,
+               "note": "attention: 4,726,784 algorithmic bytes and 1.364 GFLOP per (image, layer) (SURVEY 8d), per-launch events"}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_sample_tokens_per_s(B, N, repeats=1)
+        cpu = cpu_sample_tokens_per_s(B, N, repeats=6)
     if rank == 0:
         h2d = sum(p.numel() * 2 for p in host_px) + ids.numel() * 8
         line = {
@@ -352,7 +384,7 @@ def run_b200(args):
             "dtype": "f16", "data": "synthetic", "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * N * 4,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernel_breakdown": breakdown, "phases": phases,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernel_breakdown": breakdown, "phases": phases, "vit": vit,
             "cpu_baseline": cpu, "impl": "b200",
         }
         print(json.dumps(line), flush=True)

@@ -223,6 +223,12 @@ uint64_t vcb_launch_count(void);
 int vcb_profile_enable(int32_t on);
 int vcb_profile_read(float* ms_by_category, uint64_t* launches_by_category, int32_t n_categories);
 
+/* The decode step's weight-streaming GEMMs alone (every layer's qkv, o, gate|up, down, then lm_head) on the bound
+ * weights with batch B, back to back as inside the decode graph, `rounds` times between two CUDA events on the
+ * launching stream (one untimed warm-up round first).  *ms_total = elapsed ms, *launches = kernels timed.  Invalidates
+ * the current KV state (call vcb_prefill again before decoding). */
+int vcb_bench_weight_stream(vcb_handle h, int32_t B, int32_t rounds, float* ms_total, int32_t* launches, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -252,6 +252,12 @@ float vcb_philox_uniform(uint64_t seed, uint32_t step, uint32_t row) {
   return static_cast<float>(philox_first_host(seed, step, row) >> 8) * (1.0f / 16777216.0f);
 }
 
+int vcb_bench_weight_stream(vcb_handle h, int32_t B, int32_t rounds, float* ms_total, int32_t* launches, void* stream) {
+  VCB_CHECK(h != nullptr, kErrInvalid, "null handle");
+  StreamGuard sg(h->e, ST(stream));
+  return engine_bench_weight_stream(h->e, B, rounds, ms_total, launches, sg.st);
+}
+
 int vcb_reset(vcb_handle h) {
   VCB_CHECK(h != nullptr, kErrInvalid, "null handle");
   return engine_reset(h->e);

@@ -930,6 +930,51 @@ int engine_decode_stream(Engine* e, int max_steps, int lookahead, engine_token_c
   return kOk;
 }
 
+// The decode step's weight-streaming GEMMs alone (per layer qkv, o, gate|up, down; then lm_head) on the bound weights,
+// back to back with PDL exactly as inside the decode graph, `rounds` times between two CUDA events.  bench.py divides the
+// algorithmic weight bytes by this for the roofline of the dominant kernel without per-launch event overhead.
+int engine_bench_weight_stream(Engine* e, int B, int rounds, float* ms_total, int* launches, cudaStream_t st) {
+  const vcb_config& c = e->cfg;
+  VCB_CHECK(B >= 1 && B <= c.max_batch && rounds >= 1 && ms_total != nullptr, kErrInvalid, "bench_weight_stream: bad arguments");
+  VCB_CUDA(cudaSetDevice(e->device));
+  VCB_TRY(engine_check_bound(e, false, true));
+  const int H = c.llm_hidden, FF = c.llm_ffn, V = c.llm_vocab;
+  cudaEvent_t a = nullptr, b = nullptr;
+  VCB_CUDA(cudaEventCreate(&a));
+  VCB_CUDA(cudaEventCreate(&b));
+  int n = 0, rc = kOk;
+  auto run = [&](const __half* X, long ldx, const DevBuf& W, __half* Y, long ldy, int N, int K, int swiglu) {
+    if (rc != kOk) return;
+    SkinnyParams s;
+    s.X = X; s.ldx = ldx; s.W = W.as<__half>(); s.Y = Y; s.ldy = ldy; s.B = B; s.N = N; s.K = K; s.swiglu = swiglu;
+    rc = skinny_gemm(s, st);
+    ++n;
+  };
+  for (int r = -1; r < rounds && rc == kOk; ++r) {  // round -1 = warm-up
+    if (r == 0) { n = 0; cudaEventRecord(a, st); }
+    for (int li = 0; li < c.llm_layers; ++li) {
+      const LlmLayerW& l = e->llm[li];
+      run(e->xnd.as<__half>(), H, l.qkv_w, e->qkvd.as<__half>(), 3 * H, 3 * H, H, 0);
+      run(e->attnd.as<__half>(), H, l.o_w, e->xd.as<__half>(), H, H, H, 0);
+      run(e->xnd.as<__half>(), H, l.gu_w, e->midd.as<__half>(), FF, 2 * FF, H, 1);
+      run(e->midd.as<__half>(), FF, l.down_w, e->xd.as<__half>(), H, H, FF, 0);
+    }
+    run(e->xnd.as<__half>(), H, e->lm_head, e->logits.as<__half>(), V, V, H, 0);
+  }
+  cudaEventRecord(b, st);
+  cudaError_t se = cudaStreamSynchronize(st);
+  float ms = 0.f;
+  if (se == cudaSuccess) cudaEventElapsedTime(&ms, a, b);
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  e->prefilled = false;  // the decode workspaces were overwritten
+  VCB_TRY(rc);
+  VCB_CUDA(se);
+  *ms_total = ms;
+  if (launches) *launches = n;
+  return kOk;
+}
+
 int engine_reset(Engine* e) {
   e->prefilled = false;
   e->batch = 0;

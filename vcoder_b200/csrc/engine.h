@@ -107,6 +107,7 @@ int engine_set_sampling(Engine* e, int do_sample, float temperature, int top_k, 
 typedef int (*engine_token_cb)(void* user, int step, const int32_t* ids, int B);
 int engine_decode_stream(Engine* e, int max_steps, int lookahead, engine_token_cb cb, void* user, int* n_accepted,
                          cudaStream_t st);
+int engine_bench_weight_stream(Engine* e, int B, int rounds, float* ms_total, int* launches, cudaStream_t st);
 int copy_any(void* dst, const void* src, size_t bytes, cudaStream_t st);
 
 // Work always runs on a capturable (non-legacy) stream.  When the caller passes NULL / the legacy default stream,
