@@ -43,6 +43,9 @@ extern "C" {
 
 #define VCB_VARIANT_VCODER 0    /* VCoderLlavaLlamaForCausalLM   (vcoder_llava_llama.py:41)    */
 #define VCB_VARIANT_VCODER_DS 1 /* VCoderDSLlavaLlamaForCausalLM (vcoder_ds_llava_llama.py:41) */
+#define VCB_VARIANT_LLAVA 2     /* LlavaLlamaForCausalLM: RGB only (llava_llama.py:41, llava_arch.py:85-199) */
+#define VCB_VARIANT_VCODER_IT 3 /* VCoderITLlavaLlamaForCausalLM: RGB + optional seg (vcoder_it_llava_llama.py:41,
+                                   vcoder_it_llava_arch.py:128-277) */
 
 typedef uint16_t vcb_half;
 typedef struct vcb_engine* vcb_handle;
@@ -137,8 +140,9 @@ int vcb_op_sample_f16(const vcb_half* logits_dev, int32_t B, int32_t V, float te
 /* ---- host-only logic ------------------------------------------------------------------------ */
 
 /* The splice plan of prepare_inputs_labels_for_multimodal (vcoder_ds_llava_arch.py:175-312 /
- * vcoder_llava_arch.py:182-294) for ids_host [B,T].  depth_nonzero_host: NULL when depths is None, else B bytes
- * (`mean(depth) != 0`).  plan_out (capacity plan_cap int32) receives B*out_len entries:
+ * vcoder_llava_arch.py:182-294 / llava_arch.py:117-199 / vcoder_it_llava_arch.py:165-277) for ids_host [B,T].
+ * depth_nonzero_host: VCoder-DS: NULL when depths is None, else B bytes (`mean(depth) != 0`); VCoder-IT: the same for the
+ * seg maps (`mean(seg) != 0`, is_seg_zero), NULL when segs is None; ignored by the other variants.  plan_out (capacity plan_cap int32) receives B*out_len entries:
  *   >= 0 token id, -1 zero pad, <= -2 row -(v+2) of the feature buffer laid out [kind(rgb,seg,depth)][B][1+P] (row 0 of
  *   each image is the CLS token and is never referenced).  Needs no GPU. */
 int vcb_splice_plan(int32_t variant, const int64_t* ids_host, int32_t B, int32_t T, int32_t n_patches, int32_t has_seg,

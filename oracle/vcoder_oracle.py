@@ -134,16 +134,29 @@ class SpliceError(Exception):
     pass
 
 
-def splice_plan(ids: Sequence[Sequence[int]], variant_ds: bool, has_seg: bool, depth_nonzero: Optional[Sequence[bool]]
+V_VCODER, V_DS, V_LLAVA, V_IT = 0, 1, 2, 3  # == VCB_VARIANT_* (include/vcoder_b200.h)
+
+
+def splice_plan(ids: Sequence[Sequence[int]], variant_ds: bool, has_seg: bool, depth_nonzero: Optional[Sequence[bool]],
+                variant: Optional[int] = None, seg_nonzero: Optional[Sequence[bool]] = None
                 ) -> List[List[Tuple[str, object]]]:
-    """depth_nonzero: None when depths is None, else per-sample `mean(depth) != 0` (is_depth_zero, :161)."""
+    """depth_nonzero: None when depths is None, else per-sample `mean(depth) != 0` (is_depth_zero, :161).
+    variant (overrides variant_ds): V_VCODER vcoder_llava_arch.py:182-294 | V_DS vcoder_ds_llava_arch.py:175-312 |
+    V_LLAVA llava_arch.py:117-199 | V_IT vcoder_it_llava_arch.py:165-277 (seg_nonzero: per-sample `mean(seg) != 0`,
+    is_seg_zero :148; None when seg_images is None, which the reference treats as all-zero :158)."""
+    v = variant if variant is not None else (V_DS if variant_ds else V_VCODER)
     plans = []
     cur_image_idx = cur_seg_idx = cur_depth_idx = 0
     for row in ids:
         cur = list(int(t) for t in row)
         n_img = sum(1 for t in cur if t == IMAGE_TOKEN_INDEX)
         n_seg = sum(1 for t in cur if t == SEG_TOKEN_INDEX)
-        dummy = (n_img == 0 and n_seg == 0) if variant_ds else (n_img == 0 or n_seg == 0)  # ds:181 vs vcoder:187
+        if v == V_DS:
+            dummy = n_img == 0 and n_seg == 0  # ds:181
+        elif v == V_VCODER:
+            dummy = n_img == 0 or n_seg == 0  # vcoder:187
+        else:
+            dummy = n_img == 0  # llava_arch.py:118, vcoder_it_llava_arch.py:169
         if dummy:
             # text-only branch: embeds every id as is; a negative special id hits nn.Embedding -> IndexError (F11)
             if any(t < 0 for t in cur):
@@ -161,16 +174,28 @@ def splice_plan(ids: Sequence[Sequence[int]], variant_ds: bool, has_seg: bool, d
             segs.append(("image", cur_image_idx))
             cur_image_idx += 1
             cur = cur[i + 1:]
-        if has_seg:
+        if v in (V_VCODER, V_DS) and has_seg:
             while SEG_TOKEN_INDEX in cur:
                 i = cur.index(SEG_TOKEN_INDEX)
-                if not variant_ds:
+                if v == V_VCODER:
                     segs.append(("text", cur[:i]))  # vcoder_llava_arch.py:236
                 # DS drops the ids before the seg token (vcoder_ds_llava_arch.py:233-244)
                 segs.append(("seg", cur_seg_idx))
                 cur_seg_idx += 1
                 cur = cur[i + 1:]
-        if variant_ds:
+        elif v == V_IT:
+            seg_zero = not (has_seg and seg_nonzero is not None and bool(seg_nonzero[cur_seg_idx]))  # :148, :158
+            if not seg_zero:
+                if SEG_TOKEN_INDEX not in cur:
+                    cur_seg_idx += 1  # :212-215 (appends an empty slice of the seg features)
+                while SEG_TOKEN_INDEX in cur:
+                    i = cur.index(SEG_TOKEN_INDEX)
+                    segs.append(("seg", cur_seg_idx))  # ids before the seg token are dropped, as in DS (:216-226)
+                    cur_seg_idx += 1
+                    cur = cur[i + 1:]
+            else:
+                cur_seg_idx += 1  # :227-228; a remaining <seg> id then reaches embed_tokens -> IndexError
+        if v == V_DS:
             nz = bool(depth_nonzero[cur_depth_idx]) if depth_nonzero is not None else False
             if nz:
                 while DEPTH_TOKEN_INDEX in cur:
@@ -191,11 +216,12 @@ def splice_plan(ids: Sequence[Sequence[int]], variant_ds: bool, has_seg: bool, d
 
 
 def splice_embeds(ids, sd, image_feats, seg_feats, depth_feats, variant_ds: bool,
-                  depth_nonzero: Optional[Sequence[bool]]) -> torch.Tensor:
+                  depth_nonzero: Optional[Sequence[bool]], variant: Optional[int] = None,
+                  seg_nonzero: Optional[Sequence[bool]] = None) -> torch.Tensor:
     """-> inputs_embeds [B, T', H] fp32.  Ragged results raise (the reference crashes with NameError on the
     attention-mask rebuild when labels is None: vcoder_ds_llava_arch.py:292-300)."""
     emb = _f(sd["model.embed_tokens.weight"])  # vcoder_lm_emb is a clone of embed_tokens (:173, SURVEY F7)
-    plans = splice_plan(ids, variant_ds, seg_feats is not None, depth_nonzero)
+    plans = splice_plan(ids, variant_ds, seg_feats is not None, depth_nonzero, variant, seg_nonzero)
     rows = []
     for segs in plans:
         parts = []
@@ -304,14 +330,16 @@ def llama_forward(x: torch.Tensor, sd, g, cache: KVCache, last_only: bool = True
 #     GenerationMixin greedy: next = argmax(logits[:, -1]))
 # ---------------------------------------------------------------------------------------------------------
 def prefill_embeds(ids, sd, g, images, segs, depths):
-    variant_ds = g.variant == 1
+    variant_ds = g.variant == V_DS
     img_f = encode_images(images, sd, g)
-    seg_f = encode_seg_images(segs, sd, g) if segs is not None else None
-    dep_f, nz = None, None
+    seg_f = encode_seg_images(segs, sd, g) if (segs is not None and g.variant != V_LLAVA) else None
+    dep_f, nz, snz = None, None, None
     if variant_ds and depths is not None:
         nz = [bool(_f(d).mean() != 0) for d in depths]  # is_depth_zero (vcoder_ds_llava_arch.py:161)
         dep_f = encode_depth_images(depths, sd, g)
-    return splice_embeds(ids, sd, img_f, seg_f, dep_f, variant_ds, nz)
+    if g.variant == V_IT and segs is not None:
+        snz = [bool(_f(x).mean() != 0) for x in segs]  # is_seg_zero (vcoder_it_llava_arch.py:148)
+    return splice_embeds(ids, sd, img_f, seg_f, dep_f, variant_ds, nz, g.variant, snz)
 
 
 def greedy_generate(ids, sd, g, images, segs, depths, max_new_tokens: int, return_logits: bool = False):

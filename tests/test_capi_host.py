@@ -145,3 +145,77 @@ def test_splice_plan_random_fuzz():
         assert got == want, (ds, ids.tolist(), nz)
         n_ok += want is not None
     assert n_ok > 50
+
+
+# ---- plain LLaVA (llava_arch.py:117-199) and VCoder-IT (vcoder_it_llava_arch.py:165-277) splice rules ----
+def _oracle_rows_variant(ids, variant, has_seg, nz, P, B):
+    plans = orc.splice_plan(ids, False, has_seg, nz if variant == synth.VARIANT_VCODER_DS else None, variant=variant,
+                            seg_nonzero=nz if variant == synth.VARIANT_VCODER_IT else None)
+    kind = {"image": 0, "seg": 1, "depth": 2}
+    rows = []
+    for segs in plans:
+        r = []
+        for k, payload in segs:
+            if k == "text":
+                r += list(payload)
+            else:
+                if payload >= B:  # image_features[cur_image_idx] past the batch: the reference's IndexError
+                    raise IndexError(payload)
+                base = (kind[k] * B + payload) * (P + 1) + 1
+                r += [-(base + p) - 2 for p in range(P)]
+        rows.append(r)
+    return rows
+
+
+def test_splice_plan_llava_and_it_known_cases():
+    P = 4
+    L, IT = synth.VARIANT_LLAVA, synth.VARIANT_VCODER_IT
+    img = [-(1 + p) - 2 for p in range(P)]
+    seg = [-((1 * 1 + 0) * (P + 1) + 1 + p) - 2 for p in range(P)]
+    assert splice_plan(L, [[1, I, 7, 9]], P, False, None).tolist() == [[1] + img + [7, 9]]
+    assert splice_plan(L, [[1, 2, 3]], P, False, None).tolist() == [[1, 2, 3]]  # no <image>: plain text
+    with pytest.raises(_lib.VcbError) as ei:  # LLaVA never consumes <seg>: it reaches embed_tokens
+        splice_plan(L, [[1, I, S, 9]], P, False, None)
+    assert ei.value.code == -6
+    # IT: ids between <image> and <seg> are dropped; zero seg map skips the seg splice
+    assert splice_plan(IT, [[1, I, 7, S, 9]], P, True, [True]).tolist() == [[1] + img + seg + [9]]
+    assert splice_plan(IT, [[1, I, 7, 9]], P, True, [True]).tolist() == [[1] + img + [7, 9]]
+    assert splice_plan(IT, [[1, I, 7, 9]], P, True, [False]).tolist() == [[1] + img + [7, 9]]
+    assert splice_plan(IT, [[1, I, 7, 9]], P, False, None).tolist() == [[1] + img + [7, 9]]
+    with pytest.raises(_lib.VcbError) as ei:
+        splice_plan(IT, [[1, I, S, 9]], P, True, [False])
+    assert ei.value.code == -6
+    with pytest.raises(_lib.VcbError) as ei:  # segs=None is treated as all-zero (:158)
+        splice_plan(IT, [[1, I, S, 9]], P, False, None)
+    assert ei.value.code == -6
+
+
+def test_splice_plan_fuzz_llava_and_it():
+    rng = np.random.RandomState(1)
+    P = 3
+    n_ok = 0
+    for trial in range(300):
+        variant = [synth.VARIANT_LLAVA, synth.VARIANT_VCODER_IT][rng.randint(2)]
+        B = rng.randint(1, 4)
+        T = rng.randint(3, 9)
+        ids = rng.randint(3, 50, size=(B, T)).astype(np.int64)
+        specials = [[I], [I, S], [I, I], [S, I], [I, S, S], []][rng.randint(6)]
+        pos = sorted(rng.choice(np.arange(1, T), size=min(len(specials), T - 1), replace=False))
+        for b in range(B):
+            for p, s in zip(pos, specials):
+                ids[b, p] = s
+        has_seg = variant == synth.VARIANT_VCODER_IT and bool(rng.randint(4))
+        nz = [bool(rng.randint(2)) for _ in range(B)] if has_seg else None
+        try:
+            want = _oracle_rows_variant(ids.tolist(), variant, has_seg, nz, P, B)
+        except (orc.SpliceError, IndexError):
+            want = None
+        if want is not None and len({len(r) for r in want}) > 1:
+            want = None
+        try:
+            got = splice_plan(variant, ids, P, has_seg, nz).tolist()
+        except _lib.VcbError:
+            got = None
+        assert got == want, (variant, ids.tolist(), has_seg, nz)
+        n_ok += want is not None
+    assert n_ok > 50

@@ -161,14 +161,16 @@ def test_attention_vit(B, S, heads, scale_q):
 # ---------------------------------------------------------------------------------------------------------------
 # engine level, tiny geometry: against the oracle AND the fixtures written by the reference itself
 # ---------------------------------------------------------------------------------------------------------------
-def _tiny(variant):
+def _tiny(variant, fname=None):
     g = synth.PRESETS["tiny"].with_variant(variant)
     sd = synth.make_state_dict(g, seed=0)
-    fname = "tiny_ds.npz" if variant == synth.VARIANT_VCODER_DS else "tiny_vcoder.npz"
+    fname = fname or {synth.VARIANT_VCODER_DS: "tiny_ds.npz", synth.VARIANT_VCODER: "tiny_vcoder.npz",
+                      synth.VARIANT_LLAVA: "tiny_llava.npz", synth.VARIANT_VCODER_IT: "tiny_it.npz"}[variant]
     z = np.load(os.path.join(os.path.dirname(__file__), "golden", fname))
     assert synth.state_dict_digest(sd) == str(z["weights_digest"])
     B = z["ids"].shape[0]
-    images, segs = synth.make_pixels(g, B, 1), synth.make_pixels(g, B, 2)
+    images = synth.make_pixels(g, B, 1)
+    segs = synth.make_pixels(g, B, 2) if variant != synth.VARIANT_LLAVA else None
     depths = synth.make_pixels(g, B, 3) if variant == synth.VARIANT_VCODER_DS else None
     eng = Engine(g, max_batch=B, max_seq_len=128)
     eng.bind(sd)
@@ -192,13 +194,22 @@ def check_greedy(got_ids, got_logits, ref_ids, ref_logits, logit_tol):
     return alive
 
 
-@pytest.mark.parametrize("variant", [synth.VARIANT_VCODER_DS, synth.VARIANT_VCODER])
-def test_tiny_against_reference_golden(variant):
-    g, sd, z, eng, ids, images, segs, depths = _tiny(variant)
+@pytest.mark.parametrize("variant,fname", [(synth.VARIANT_VCODER_DS, None), (synth.VARIANT_VCODER, None),
+                                           # plain LLaVA-1.5 and VCoder-IT, fixtures written by the reference
+                                           (synth.VARIANT_LLAVA, None), (synth.VARIANT_VCODER_IT, None),
+                                           (synth.VARIANT_VCODER_IT, "tiny_it_noseg.npz")])
+def test_tiny_against_reference_golden(variant, fname):
+    g, sd, z, eng, ids, images, segs, depths = _tiny(variant, fname)
+    if fname == "tiny_it_noseg.npz":
+        segs[0] = 0  # is_seg_zero for row 0 (vcoder_it_llava_arch.py:148); row 1's seg map is encoded but not spliced
     tower = eng.tower_forward(images)
     assert rel_rms(tower, torch.from_numpy(z["tower_features"])) <= 4e-3
     assert rel_rms(eng.encode(0, images), torch.from_numpy(z["image_features"])) <= 4e-3
-    assert rel_rms(eng.encode(1, segs), torch.from_numpy(z["seg_features"])) <= 4e-3
+    if segs is not None:
+        assert rel_rms(eng.encode(1, segs), torch.from_numpy(z["seg_features"])) <= 4e-3
+    else:
+        with pytest.raises(_lib.VcbError):
+            eng.encode(1, images)
     if depths is not None:
         assert rel_rms(eng.encode(2, depths), torch.from_numpy(z["depth_features"])) <= 4e-3  # via seg_mm_projector
     pre = eng.prefill(ids, images, segs, depths, want_logits=True, want_embeds=True)

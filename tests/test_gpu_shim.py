@@ -93,3 +93,35 @@ def test_reference_error_behaviour():
         m2.generate(torch.tensor([[1, I, S, 7]]), images=images, segs=segs, do_sample=True, temperature=0.0, max_new_tokens=2)
     with pytest.raises(NotImplementedError):
         m2.generate(torch.tensor([[1, I, S, 7]]), images=images, segs=segs, num_beams=2, max_new_tokens=2)
+
+
+def test_f4_variant_classes_and_dispatch():
+    """class dispatch by model name in the reference's order (builder.py:93-108) and the LLaVA / VCoder-IT
+    shims reproducing the reference's own greedy ids (fixtures written by the reference)."""
+    from vcoder_b200.model import build_model, variant_from_name
+    assert variant_from_name("vcoder_it_llava-v1.5-7b") == synth.VARIANT_VCODER_IT
+    assert variant_from_name("vcoder_ds_llava-v1.5-7b") == synth.VARIANT_VCODER_DS
+    assert variant_from_name("vcoder_llava-v1.5-7b") == synth.VARIANT_VCODER
+    assert variant_from_name("llava-v1.5-7b") == synth.VARIANT_LLAVA
+    with pytest.raises(ValueError):
+        variant_from_name("vicuna-7b")
+    for name, variant, fname in (("llava-tiny", synth.VARIANT_LLAVA, "tiny_llava.npz"),
+                                 ("vcoder_it_llava-tiny", synth.VARIANT_VCODER_IT, "tiny_it.npz")):
+        g = synth.PRESETS["tiny"].with_variant(variant)
+        sd = synth.make_state_dict(g, seed=0)
+        z = np.load(os.path.join(GOLD, fname))
+        m = build_model(name, g, sd, max_batch=2, max_seq_len=128)
+        assert m.geometry.variant == variant
+        ids = torch.from_numpy(z["ids"])
+        images, segs = synth.make_pixels(g, 2, 1), synth.make_pixels(g, 2, 2)
+        n_new = z["greedy_ids"].shape[1]
+        kw = dict(images=images, max_new_tokens=n_new)
+        if variant == synth.VARIANT_VCODER_IT:
+            kw["segs"] = segs
+        out = m.generate(ids, **kw)
+        assert np.array_equal(out[:, ids.shape[1]:].cpu().numpy(), z["greedy_ids"])
+        with pytest.raises(TypeError):
+            m.generate(ids, images=images, segs=segs, depths=images, max_new_tokens=2)
+        if variant == synth.VARIANT_LLAVA:
+            with pytest.raises(TypeError):
+                m.generate(ids, images=images, segs=segs, max_new_tokens=2)

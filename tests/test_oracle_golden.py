@@ -10,7 +10,9 @@ import torch
 from oracle import vcoder_oracle as orc
 from vcoder_b200 import synth
 
-CASES = [("tiny_ds.npz", synth.VARIANT_VCODER_DS), ("tiny_vcoder.npz", synth.VARIANT_VCODER)]
+CASES = [("tiny_ds.npz", synth.VARIANT_VCODER_DS), ("tiny_vcoder.npz", synth.VARIANT_VCODER),
+         # plain LLaVA-1.5 (llava_arch.py) and VCoder-IT (vcoder_it_llava_arch.py), same generator script
+         ("tiny_llava.npz", synth.VARIANT_LLAVA), ("tiny_it.npz", synth.VARIANT_VCODER_IT)]
 
 
 def _load(golden_dir, fname, variant):
@@ -20,7 +22,7 @@ def _load(golden_dir, fname, variant):
     assert synth.state_dict_digest(sd) == str(z["weights_digest"]), "seeded weight generator drifted from the fixture"
     B = z["ids"].shape[0]
     images = synth.make_pixels(g, B, 1)
-    segs = synth.make_pixels(g, B, 2)
+    segs = synth.make_pixels(g, B, 2) if variant != synth.VARIANT_LLAVA else None
     depths = synth.make_pixels(g, B, 3) if variant == synth.VARIANT_VCODER_DS else None
     return z, g, sd, images, segs, depths
 
@@ -47,7 +49,8 @@ def test_tower_hidden_states_and_select(golden_dir, fname, variant):
 def test_encoders(golden_dir, fname, variant):
     z, g, sd, images, segs, depths = _load(golden_dir, fname, variant)
     _close(orc.encode_images(images, sd, g), z["image_features"])
-    _close(orc.encode_seg_images(segs, sd, g), z["seg_features"])
+    if segs is not None:
+        _close(orc.encode_seg_images(segs, sd, g), z["seg_features"])
     if depths is not None:
         # depth goes through seg_mm_projector
         _close(orc.encode_depth_images(depths, sd, g), z["depth_features"])
@@ -59,8 +62,9 @@ def test_splice(golden_dir, fname, variant):
     x = orc.prefill_embeds(torch.from_numpy(z["ids"]), sd, g, images, segs, depths)
     assert tuple(x.shape) == z["inputs_embeds"].shape
     T_ids = z["ids"].shape[1]
-    n_special = 3 if variant == synth.VARIANT_VCODER_DS else 2
-    assert x.shape[1] == T_ids - n_special + 2 * g.n_patches  # depth computed then dropped
+    n_special = {synth.VARIANT_VCODER_DS: 3, synth.VARIANT_LLAVA: 1}.get(variant, 2)
+    n_vis = 1 if variant == synth.VARIANT_LLAVA else 2
+    assert x.shape[1] == T_ids - n_special + n_vis * g.n_patches  # depth computed then dropped
     _close(x, z["inputs_embeds"])
     assert z["spliced_mask"].all()
 
@@ -114,3 +118,28 @@ def test_splice_plan_quirks():
     assert p == [("text", [1]), ("image", 0), ("text", [9])]
     # text-only prompt: split in halves, both embedded
     assert orc.splice_plan([[1, 2, 3]], True, True, None)[0] == [("text", [1]), ("text", [2, 3])]
+
+
+def test_vcoder_it_zero_seg_and_missing_seg_token(golden_dir):
+    """VCoder-IT (f4): prompt with <image> only; row 0's seg map is all-zero (skipped, vcoder_it_llava_arch.py:148/:227),
+    row 1's is encoded but contributes an empty slice (:212-215).  Fixture written by the reference itself."""
+    z = np.load(os.path.join(golden_dir, "tiny_it_noseg.npz"))
+    g = synth.PRESETS["tiny"].with_variant(synth.VARIANT_VCODER_IT)
+    sd = synth.make_state_dict(g, seed=0)
+    assert synth.state_dict_digest(sd) == str(z["weights_digest"])
+    images, segs = synth.make_pixels(g, 2, 1), synth.make_pixels(g, 2, 2)
+    segs[0] = 0
+    ids = torch.from_numpy(z["ids"])
+    x = orc.prefill_embeds(ids, sd, g, images, segs, None)
+    assert x.shape[1] == ids.shape[1] - 1 + g.n_patches
+    _close(x, z["inputs_embeds"])
+    new = orc.greedy_generate(ids, sd, g, images, segs, None, max_new_tokens=z["greedy_ids"].shape[1])
+    assert np.array_equal(new.numpy(), z["greedy_ids"])
+    # a <seg> token behind an all-zero seg map reaches embed_tokens: the reference's IndexError
+    I, S = orc.IMAGE_TOKEN_INDEX, orc.SEG_TOKEN_INDEX
+    with pytest.raises(orc.SpliceError):
+        orc.splice_plan([[1, I, S, 9]], False, True, None, variant=orc.V_IT, seg_nonzero=[False])
+    p = orc.splice_plan([[1, I, 7, S, 9]], False, True, None, variant=orc.V_IT, seg_nonzero=[True])[0]
+    assert p == [("text", [1]), ("image", 0), ("seg", 0), ("text", [9])]  # the 7 before <seg> is dropped, as in DS
+    p = orc.splice_plan([[1, I, 7, 9]], False, False, None, variant=orc.V_LLAVA)[0]
+    assert p == [("text", [1]), ("image", 0), ("text", [7, 9])]

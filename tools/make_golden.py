@@ -40,7 +40,10 @@ AutoModelForCausalLM.register = classmethod(lambda cls, cc, mc, exist_ok=False: 
 
 from transformers import CLIPImageProcessor, CLIPVisionConfig, CLIPVisionModel  # noqa: E402
 
-from vcoder_llava.model import (VCoderDSLlavaLlamaForCausalLM, VCoderLlavaLlamaForCausalLM)  # noqa: E402
+from vcoder_llava.model import (LlavaLlamaForCausalLM, VCoderDSLlavaLlamaForCausalLM,  # noqa: E402
+                                VCoderITLlavaLlamaForCausalLM, VCoderLlavaLlamaForCausalLM)
+from vcoder_llava.model.language_model.llava_llama import LlavaConfig  # noqa: E402
+from vcoder_llava.model.language_model.vcoder_it_llava_llama import VCoderITLlavaConfig  # noqa: E402
 from vcoder_llava.model.language_model.vcoder_ds_llava_llama import VCoderDSLlavaConfig  # noqa: E402
 from vcoder_llava.model.language_model.vcoder_llava_llama import VCoderLlavaConfig  # noqa: E402
 from vcoder_llava import mm_utils  # noqa: E402
@@ -64,6 +67,14 @@ def build_reference_model(g, sd, tower_dir):
     if g.variant == synth.VARIANT_VCODER_DS:
         cfg = VCoderDSLlavaConfig(depth_mm_projector_type="mlp2x_gelu", depth_mm_hidden_size=g.vit_hidden, **kw)
         model = VCoderDSLlavaLlamaForCausalLM(cfg)
+    elif g.variant == synth.VARIANT_LLAVA:  # plain LLaVA-1.5 (model/llava_arch.py)
+        for k in ("seg_mm_projector_type", "seg_mm_hidden_size", "mm_vcoder_lm_emb", "use_mm2_proj"):
+            kw.pop(k)
+        model = LlavaLlamaForCausalLM(LlavaConfig(**kw))
+    elif g.variant == synth.VARIANT_VCODER_IT:  # f4: VCoder-IT (model/vcoder_it_llava_arch.py)
+        for k in ("mm_vcoder_lm_emb", "use_mm2_proj"):
+            kw.pop(k)
+        model = VCoderITLlavaLlamaForCausalLM(VCoderITLlavaConfig(**kw))
     else:
         cfg = VCoderLlavaConfig(**kw)
         model = VCoderLlavaLlamaForCausalLM(cfg)
@@ -82,14 +93,18 @@ def build_reference_model(g, sd, tower_dir):
 
 
 @torch.no_grad()
-def run_variant(g, out_path, batch=2, n_new=6, seed=0):
+def run_variant(g, out_path, batch=2, n_new=6, seed=0, zero_seg_rows=(), ids=None):
     sd = synth.make_state_dict(g, seed=seed)
     with tempfile.TemporaryDirectory() as td:
         model = build_reference_model(g, sd, td)
-        ids = synth.make_prompt_ids(g, batch, seed=seed, n_before=5, n_after=4)
+        if ids is None:
+            ids = synth.make_prompt_ids(g, batch, seed=seed, n_before=5, n_after=4)
         images = synth.make_pixels(g, batch, 1).float()
-        segs = synth.make_pixels(g, batch, 2).float()
+        segs = synth.make_pixels(g, batch, 2).float() if g.variant != synth.VARIANT_LLAVA else None
         depths = synth.make_pixels(g, batch, 3).float() if g.variant == synth.VARIANT_VCODER_DS else None
+        if zero_seg_rows:  # VCoder-IT is_seg_zero path (vcoder_it_llava_arch.py:148): an all-zero seg map is skipped
+            for r in zero_seg_rows:
+                segs[r] = 0
         tower = model.get_vision_tower()
         out = {"ids": ids.numpy(), "weights_digest": np.array(synth.state_dict_digest(sd))}
         # a1: tower + all hidden states of the first image batch
@@ -98,13 +113,16 @@ def run_variant(g, out_path, batch=2, n_new=6, seed=0):
         out["tower_features"] = tower(images).numpy()
         # a2/a3
         out["image_features"] = model.encode_images(images).numpy()
-        out["seg_features"] = model.encode_seg_images(segs).numpy()
+        if segs is not None:
+            out["seg_features"] = model.encode_seg_images(segs).numpy()
         if depths is not None:
             out["depth_features"] = model.encode_depth_images(depths).numpy()
         # a4: splice
         mask = torch.ones_like(ids)
         if depths is not None:
             _, m2, _, embeds, _ = model.prepare_inputs_labels_for_multimodal(ids, mask, None, None, images, segs, depths)
+        elif segs is None:
+            _, m2, _, embeds, _ = model.prepare_inputs_labels_for_multimodal(ids, mask, None, None, images)
         else:
             _, m2, _, embeds, _ = model.prepare_inputs_labels_for_multimodal(ids, mask, None, None, images, segs)
         out["inputs_embeds"] = embeds.numpy()
@@ -112,8 +130,10 @@ def run_variant(g, out_path, batch=2, n_new=6, seed=0):
         # a5/a6 route (i) FIRST: the reference generate() path (forward + splice each step, no cache).
         # (Calling HF's model.model(..., output_hidden_states=True) beforehand perturbs later generate() calls under
         #  transformers 5.5.0, so per-layer hidden states below are captured with plain forward hooks instead.)
-        kw = dict(images=images, segs=segs, do_sample=False, use_cache=False, max_new_tokens=n_new,
+        kw = dict(images=images, do_sample=False, use_cache=False, max_new_tokens=n_new,
                   pad_token_id=0, eos_token_id=None)
+        if segs is not None:
+            kw["segs"] = segs
         if depths is not None:
             kw["depths"] = depths
         gen = model.generate(ids, **kw)
@@ -169,6 +189,16 @@ if __name__ == "__main__":
     gold = os.path.join(ROOT, "tests", "golden")
     os.makedirs(gold, exist_ok=True)
     torch.manual_seed(0)
-    run_variant(synth.PRESETS["tiny"].with_variant(synth.VARIANT_VCODER_DS), os.path.join(gold, "tiny_ds.npz"))
-    run_variant(synth.PRESETS["tiny"].with_variant(synth.VARIANT_VCODER), os.path.join(gold, "tiny_vcoder.npz"))
+    only_new = "--only-new" in sys.argv  # keep the committed a-row fixtures byte-identical
+    if not only_new:
+        run_variant(synth.PRESETS["tiny"].with_variant(synth.VARIANT_VCODER_DS), os.path.join(gold, "tiny_ds.npz"))
+        run_variant(synth.PRESETS["tiny"].with_variant(synth.VARIANT_VCODER), os.path.join(gold, "tiny_vcoder.npz"))
     tokenizer_order_fixture(os.path.join(gold, "tokenizer_order.npz"))
+    # SURVEY §8 f4 variants
+    run_variant(synth.PRESETS["tiny"].with_variant(synth.VARIANT_LLAVA), os.path.join(gold, "tiny_llava.npz"))
+    run_variant(synth.PRESETS["tiny"].with_variant(synth.VARIANT_VCODER_IT), os.path.join(gold, "tiny_it.npz"))
+    # VCoder-IT with no <seg> token in the prompt: row 0 has an all-zero seg map (is_seg_zero, :148/:227), row 1 a
+    # non-zero one that is encoded but spliced as an empty slice (:212-215)
+    g_it = synth.PRESETS["tiny"].with_variant(synth.VARIANT_VCODER_IT)
+    run_variant(g_it, os.path.join(gold, "tiny_it_noseg.npz"), zero_seg_rows=(0,),
+                ids=synth.make_prompt_ids(g_it, 2, seed=0, n_before=5, n_after=4, specials=[synth.IMAGE_TOKEN_INDEX]))

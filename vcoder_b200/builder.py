@@ -15,7 +15,7 @@ from typing import Dict
 import torch
 
 from . import synth
-from .model import build_model
+from .model import build_model, variant_from_name
 from .synth import ModelGeometry
 
 _VT = "model.vision_tower.vision_tower."
@@ -55,13 +55,7 @@ def load_pretrained_model(model_path, model_base, model_name, load_8bit=False, l
         raise NotImplementedError("bitsandbytes 8/4-bit loading is SURVEY §8 row f4 (next); fp16 only")
     if model_base is not None:
         raise NotImplementedError("LoRA / delta checkpoints: merge offline with the reference's scripts/merge_lora_weights.py")
-    name = model_name.lower()
-    if "vcoder_ds_llava" in name:
-        variant = synth.VARIANT_VCODER_DS
-    elif "vcoder_llava" in name:
-        variant = synth.VARIANT_VCODER
-    else:
-        raise ValueError(f"{model_name}: only vcoder_llava / vcoder_ds_llava models are on the accelerated path")
+    variant = variant_from_name(model_name)
     cfg = json.load(open(os.path.join(model_path, "config.json")))
     tower_path = cfg["mm_vision_tower"]
     vcfg_path = os.path.join(tower_path, "config.json")
@@ -84,7 +78,8 @@ def load_pretrained_model(model_path, model_base, model_name, load_8bit=False, l
     try:
         from transformers import CLIPImageProcessor
         image_processor = CLIPImageProcessor.from_pretrained(tower_path)
-        seg_image_processor = image_processor  # builder.py:146-151: same processor object for every modality
+        # builder.py:146-151: same processor object for every modality the class has
+        seg_image_processor = image_processor if variant != synth.VARIANT_LLAVA else None
         depth_image_processor = image_processor if variant == synth.VARIANT_VCODER_DS else None
     except Exception:
         pass

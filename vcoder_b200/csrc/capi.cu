@@ -118,7 +118,7 @@ int vcb_op_attention_vit_f16(const vcb_half* qkv, int32_t B, int32_t S, int32_t 
 int vcb_splice_plan(int32_t variant, const int64_t* ids, int32_t B, int32_t T, int32_t n_patches, int32_t has_seg,
                     const uint8_t* depth_nonzero, int32_t* plan_out, int64_t plan_cap, int32_t* out_len) {
   VCB_CHECK(ids != nullptr && out_len != nullptr && B >= 1 && T >= 1, kErrInvalid, "vcb_splice_plan: bad arguments");
-  VCB_CHECK(variant == VCB_VARIANT_VCODER || variant == VCB_VARIANT_VCODER_DS, kErrInvalid, "bad variant");
+  VCB_CHECK(variant >= VCB_VARIANT_VCODER && variant <= VCB_VARIANT_VCODER_IT, kErrInvalid, "bad variant");
   std::vector<int32_t> plan;
   int len = 0;
   VCB_TRY(splice_plan_host(variant, ids, B, T, n_patches, has_seg, depth_nonzero, &plan, &len, nullptr));
@@ -171,6 +171,9 @@ int vcb_encode(vcb_handle h, int32_t modality, const vcb_half* pixels, int32_t n
   VCB_CHECK(h != nullptr && pixels != nullptr && out != nullptr, kErrInvalid, "vcb_encode: null argument");
   VCB_CHECK(modality >= 0 && modality <= 2, kErrInvalid, "vcb_encode: modality must be 0 (rgb), 1 (seg) or 2 (depth)");
   Engine* e = h->e;
+  VCB_CHECK(modality == 0 || e->cfg.variant != VCB_VARIANT_LLAVA, kErrInvalid, "vcb_encode: LLaVA has no seg projector");
+  VCB_CHECK(modality != 2 || e->cfg.variant == VCB_VARIANT_VCODER_DS, kErrInvalid,
+            "vcb_encode: encode_depth_images exists on VCoder-DS only");
   VCB_CUDA(cudaSetDevice(e->device));
   VCB_TRY(engine_check_bound(e, true, true));
   VCB_CHECK(n >= 1 && n <= e->vit_max_images, kErrInvalid, "vcb_encode: n must be in [1, 3*max_batch]");

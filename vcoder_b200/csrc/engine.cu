@@ -81,7 +81,7 @@ Engine::~Engine() {
 int engine_create(const vcb_config* c, int device, Engine** out) {
   VCB_CHECK(c != nullptr && out != nullptr, kErrInvalid, "vcb_create: null argument");
   VCB_CHECK(c->struct_size == static_cast<int32_t>(sizeof(vcb_config)), kErrInvalid, "vcb_create: struct_size mismatch");
-  VCB_CHECK(c->variant == VCB_VARIANT_VCODER || c->variant == VCB_VARIANT_VCODER_DS, kErrInvalid, "bad variant");
+  VCB_CHECK(c->variant >= VCB_VARIANT_VCODER && c->variant <= VCB_VARIANT_VCODER_IT, kErrInvalid, "bad variant");
   VCB_CHECK(c->vit_hidden == c->vit_heads * 64, kErrInvalid, "CLIP head_dim must be 64");
   VCB_CHECK(c->llm_hidden == c->llm_heads * 128, kErrInvalid, "LLaMA head_dim must be 128");
   VCB_CHECK(c->vit_hidden % 64 == 0 && c->vit_ffn % 64 == 0 && c->llm_hidden % 64 == 0 && c->llm_ffn % 64 == 0,
@@ -323,8 +323,10 @@ int engine_check_bound(Engine* e, bool need_vision, bool need_llm) {
     }
   }
   if (need_llm) {
-    for (const char* pj : {"model.mm_projector.", "model.seg_mm_projector."})
+    for (const char* pj : {"model.mm_projector.", "model.seg_mm_projector."}) {
+      if (c.variant == VCB_VARIANT_LLAVA && std::strcmp(pj, "model.seg_mm_projector.") == 0) continue;  // llava_arch.py:36-38
       for (const char* s : {"0.weight", "0.bias", "2.weight", "2.bias"}) need.push_back(std::string(pj) + s);
+    }
     need.push_back("model.embed_tokens.weight");
     need.push_back("model.norm.weight");
     need.push_back("lm_head.weight");
@@ -429,12 +431,15 @@ int engine_project(Engine* e, int row_begin, int row_end, const ProjW& w, cudaSt
 // splice planner (host)
 // ------------------------------------------------------------------------------------------------------------
 int splice_plan_host(int variant, const int64_t* ids, int B, int T, int n_patches, int has_seg,
-                     const uint8_t* depth_nonzero, std::vector<int32_t>* plan, int* out_len, bool* depth_flag_needed) {
-  const bool ds = variant == VCB_VARIANT_VCODER_DS;
+                     const uint8_t* nonzero, std::vector<int32_t>* plan, int* out_len, bool* flag_needed) {
+  // `nonzero`: VCoder-DS per-sample mean(depth) != 0 (is_depth_zero, vcoder_ds_llava_arch.py:161), VCoder-IT per-sample
+  // mean(seg) != 0 (is_seg_zero, vcoder_it_llava_arch.py:148); null = that modality was not passed
+  const bool ds = variant == VCB_VARIANT_VCODER_DS, it = variant == VCB_VARIANT_VCODER_IT;
+  const bool vc = variant == VCB_VARIANT_VCODER;
   const int tokens = n_patches + 1;
   std::vector<std::vector<int32_t>> rows(B);
   int cur_img = 0, cur_seg = 0, cur_depth = 0;
-  if (depth_flag_needed) *depth_flag_needed = false;
+  if (flag_needed) *flag_needed = false;
   auto push_text = [&](std::vector<int32_t>& r, const int64_t* p, int n) -> int {
     for (int i = 0; i < n; ++i) {
       if (p[i] < 0) {
@@ -454,7 +459,8 @@ int splice_plan_host(int variant, const int64_t* ids, int B, int T, int n_patche
     std::vector<int32_t>& r = rows[b];
     int n_img = 0, n_seg = 0;
     for (int t = 0; t < T; ++t) { n_img += row[t] == VCB_IMAGE_TOKEN_INDEX; n_seg += row[t] == VCB_SEG_TOKEN_INDEX; }
-    const bool dummy = ds ? (n_img == 0 && n_seg == 0) : (n_img == 0 || n_seg == 0);
+    // ds :181, vcoder :187, llava_arch.py:118 / vcoder_it_llava_arch.py:169
+    const bool dummy = ds ? (n_img == 0 && n_seg == 0) : vc ? (n_img == 0 || n_seg == 0) : (n_img == 0);
     if (dummy) {
       VCB_TRY(push_text(r, row, T));
       ++cur_img; ++cur_seg; ++cur_depth;
@@ -468,18 +474,32 @@ int splice_plan_host(int variant, const int64_t* ids, int B, int T, int n_patche
       push_feat(r, 0, cur_img++);
       pos = t + 1;
     }
-    if (has_seg) {
+    if ((ds || vc) && has_seg) {
       for (int t; (t = find(VCB_SEG_TOKEN_INDEX)) >= 0;) {
-        if (!ds) VCB_TRY(push_text(r, row + pos, t - pos));  // DS drops these ids
+        if (vc) VCB_TRY(push_text(r, row + pos, t - pos));  // DS drops these ids
         VCB_CHECK(cur_seg < B, kErrInvalid, "more <seg> tokens than seg images");
         push_feat(r, 1, cur_seg++);
         pos = t + 1;
       }
+    } else if (it) {
+      VCB_CHECK(cur_seg < B, kErrInvalid, "more seg rows consumed than seg images");
+      if (has_seg && flag_needed) *flag_needed = true;
+      const bool seg_nz = has_seg && nonzero != nullptr && nonzero[cur_seg] != 0;
+      if (seg_nz) {
+        if (find(VCB_SEG_TOKEN_INDEX) < 0) ++cur_seg;  // :212-215, an empty slice of the seg features
+        for (int t; (t = find(VCB_SEG_TOKEN_INDEX)) >= 0;) {
+          VCB_CHECK(cur_seg < B, kErrInvalid, "more <seg> tokens than seg images");
+          push_feat(r, 1, cur_seg++);  // the ids before <seg> are dropped, as in DS (:216-226)
+          pos = t + 1;
+        }
+      } else {
+        ++cur_seg;  // :227-228
+      }
     }
     if (ds) {
       const bool has_depth_tok = find(VCB_DEPTH_TOKEN_INDEX) >= 0;
-      if (has_depth_tok && depth_flag_needed) *depth_flag_needed = true;
-      const bool nz = depth_nonzero != nullptr && depth_nonzero[cur_depth] != 0;
+      if (has_depth_tok && flag_needed) *flag_needed = true;
+      const bool nz = nonzero != nullptr && nonzero[cur_depth] != 0;
       if (nz) {
         for (int t; (t = find(VCB_DEPTH_TOKEN_INDEX)) >= 0;) {
           VCB_TRY(push_text(r, row + pos, t - pos));
@@ -556,7 +576,8 @@ int engine_prefill(Engine* e, const int64_t* ids, int B, int T, const void* imag
   const bool ds = c.variant == VCB_VARIANT_VCODER_DS;
   const bool multimodal = images != nullptr;  // reference: `images is None` -> plain LLaMA path (arch.py:130)
   VCB_TRY(engine_check_bound(e, multimodal, true));
-  VCB_CHECK(ds || depths == nullptr, kErrInvalid, "VCoder (non-DS) takes no depth images");
+  VCB_CHECK(ds || depths == nullptr, kErrInvalid, "only VCoder-DS takes depth images");
+  VCB_CHECK(c.variant != VCB_VARIANT_LLAVA || segs == nullptr, kErrInvalid, "LLaVA takes no seg images");
   const int D = c.vit_hidden, H = c.llm_hidden, FF = c.llm_ffn, V = c.llm_vocab, S = e->S;
   const long img_halves = 3L * c.vit_image_size * c.vit_image_size;
   e->prefilled = false;
@@ -575,20 +596,24 @@ int engine_prefill(Engine* e, const int64_t* ids, int B, int T, const void* imag
     VCB_TRY(engine_tower(e, pix, kinds * B, st));
     VCB_TRY(engine_project(e, 0, B * S, e->mm, st));                // encode_images: mm_projector
     VCB_TRY(engine_project(e, B * S, kinds * B * S, e->seg, st));   // seg AND depth: seg_mm_projector (F3)
-    // ---- splice plan; the is_depth_zero flag costs a sync only when a <depth> token can actually be reached
+    // ---- splice plan; the is_depth_zero (DS) / is_seg_zero (IT) flags cost one host sync, paid only when the plan can
+    //      depend on them (DS: a <depth> token is reachable after the seg splice; IT: seg images were passed)
+    const bool it = c.variant == VCB_VARIANT_VCODER_IT;
+    const bool have_flag_modality = (ds && depths) || (it && segs);
     bool need_flag = false;
     std::vector<uint8_t> nz(B, 1);
-    int rc = splice_plan_host(c.variant, ids, B, T, e->P, segs != nullptr, (ds && depths) ? nz.data() : nullptr, &plan,
+    int rc = splice_plan_host(c.variant, ids, B, T, e->P, segs != nullptr, have_flag_modality ? nz.data() : nullptr, &plan,
                               &Tp, &need_flag);
-    if (need_flag && ds && depths) {
+    if (need_flag && have_flag_modality) {
+      const __half* flag_px = pix + (ds ? 2L : 1L) * B * img_halves;
       VCB_CUDA(cudaMemsetAsync(e->depth_sums.p, 0, B * 4, st));
-      depth_sum_kernel<<<dim3(32, B), 256, 0, st>>>(pix + 2L * B * img_halves, img_halves, e->depth_sums.as<float>());
+      depth_sum_kernel<<<dim3(32, B), 256, 0, st>>>(flag_px, img_halves, e->depth_sums.as<float>());
       VCB_CUDA(cudaGetLastError());
       VCB_TRY(copy_any(e->depth_host, e->depth_sums.p, B * 4, st));
       VCB_CUDA(cudaStreamSynchronize(st));
       for (int b = 0; b < B; ++b) {
         const __half m = __float2half_rn(e->depth_host[b] / static_cast<float>(img_halves));
-        nz[b] = (__half2float(m) != 0.f) ? 1 : 0;  // torch.mean(d) == 0 on an fp16 tensor (arch.py:161)
+        nz[b] = (__half2float(m) != 0.f) ? 1 : 0;  // torch.mean(x) == 0 on an fp16 tensor (ds arch.py:161, it arch.py:148)
       }
       rc = splice_plan_host(c.variant, ids, B, T, e->P, segs != nullptr, nz.data(), &plan, &Tp, nullptr);
     }

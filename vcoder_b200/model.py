@@ -156,8 +156,10 @@ class _VCoderBase:
             raise NotImplementedError("beam search is not on the reference's hot path (num_beams=1 everywhere)")
         if attention_mask is not None and not bool(torch.as_tensor(attention_mask).bool().all()):
             raise NotImplementedError("padded prompts: the reference itself mis-aligns the mask after the splice")
-        if self.variant == synth.VARIANT_VCODER and depths is not None:
-            raise TypeError("VCoderLlavaLlamaForCausalLM.generate() got an unexpected keyword argument 'depths'")
+        if self.variant != synth.VARIANT_VCODER_DS and depths is not None:
+            raise TypeError(f"{type(self).__name__}.generate() got an unexpected keyword argument 'depths'")
+        if self.variant == synth.VARIANT_LLAVA and segs is not None:
+            raise TypeError(f"{type(self).__name__}.generate() got an unexpected keyword argument 'segs'")
         gc = self.generation_config
         if eos_token_id is None:
             eos_token_id = gc.eos_token_id
@@ -241,11 +243,38 @@ class VCoderLlavaLlamaForCausalLM(_VCoderBase):
     model_type = "vcoder_llava"
 
 
-def build_model(model_name: str, g: ModelGeometry, state_dict=None, **kw):
-    """Class dispatch by substring of the model name, as load_pretrained_model does (builder.py:93-108)."""
+class VCoderITLlavaLlamaForCausalLM(_VCoderBase):
+    """vcoder_it_llava_llama.py:41 — RGB + optional seg map (all-zero seg maps are skipped, vcoder_it_llava_arch.py:148)."""
+    variant = synth.VARIANT_VCODER_IT
+    model_type = "vcoder_it_llava"
+
+
+class LlavaLlamaForCausalLM(_VCoderBase):
+    """llava_llama.py:41 — plain LLaVA-1.5: RGB only (llava_arch.py:85-199)."""
+    variant = synth.VARIANT_LLAVA
+    model_type = "llava"
+
+    def encode_seg_images(self, seg_images):
+        raise AttributeError("'LlavaLlamaForCausalLM' object has no attribute 'encode_seg_images'")
+
+
+def variant_from_name(model_name: str) -> int:
+    """Class dispatch by substring of the model name, in the order load_pretrained_model tests them (builder.py:93-108)."""
     name = model_name.lower()
+    if "vcoder_it_llava" in name:
+        return synth.VARIANT_VCODER_IT
     if "vcoder_ds_llava" in name:
-        return VCoderDSLlavaLlamaForCausalLM(g, state_dict, **kw)
+        return synth.VARIANT_VCODER_DS
     if "vcoder_llava" in name:
-        return VCoderLlavaLlamaForCausalLM(g, state_dict, **kw)
-    raise ValueError(f"{model_name}: only vcoder_llava / vcoder_ds_llava models are on the accelerated path")
+        return synth.VARIANT_VCODER
+    if "llava" in name:
+        return synth.VARIANT_LLAVA
+    raise ValueError(f"{model_name}: not a LLaVA-family model (plain language models are not on the accelerated path)")
+
+
+_CLASSES = {synth.VARIANT_VCODER: VCoderLlavaLlamaForCausalLM, synth.VARIANT_VCODER_DS: VCoderDSLlavaLlamaForCausalLM,
+            synth.VARIANT_LLAVA: LlavaLlamaForCausalLM, synth.VARIANT_VCODER_IT: VCoderITLlavaLlamaForCausalLM}
+
+
+def build_model(model_name: str, g: ModelGeometry, state_dict=None, **kw):
+    return _CLASSES[variant_from_name(model_name)](g, state_dict, **kw)

@@ -21,8 +21,10 @@ IMAGE_TOKEN_INDEX = -200  # reference vcoder_llava/constants.py:9
 SEG_TOKEN_INDEX = -300  # constants.py:10
 DEPTH_TOKEN_INDEX = -400  # constants.py:11
 
-VARIANT_VCODER = 0
-VARIANT_VCODER_DS = 1
+VARIANT_VCODER = 0     # VCoderLlavaLlamaForCausalLM    (RGB + seg)
+VARIANT_VCODER_DS = 1  # VCoderDSLlavaLlamaForCausalLM  (RGB + seg + depth)
+VARIANT_LLAVA = 2      # LlavaLlamaForCausalLM          (RGB only; language_model/llava_llama.py, model/llava_arch.py)
+VARIANT_VCODER_IT = 3  # VCoderITLlavaLlamaForCausalLM  (RGB + optional seg; model/vcoder_it_llava_arch.py)
 
 
 @dataclasses.dataclass(frozen=True)
@@ -110,9 +112,14 @@ def weight_specs(g: ModelGeometry):
     # projectors: mlp2x_gelu (multimodal_projector/builder.py:39-46); depth/mm2 exist in checkpoints but are never
     # called at inference — they are generated so that bind must accept and ignore them.
     H = g.llm_hidden
-    projs = ["mm_projector", "seg_mm_projector", "mm2_projector"]
-    if g.variant == VARIANT_VCODER_DS:
-        projs.insert(2, "depth_mm_projector")
+    if g.variant == VARIANT_LLAVA:
+        projs = ["mm_projector"]  # llava_arch.py:36-38
+    elif g.variant == VARIANT_VCODER_IT:
+        projs = ["mm_projector", "seg_mm_projector"]  # vcoder_it_llava_arch.py:32-38 (no mm2 / vcoder_lm_emb)
+    else:
+        projs = ["mm_projector", "seg_mm_projector", "mm2_projector"]
+        if g.variant == VARIANT_VCODER_DS:
+            projs.insert(2, "depth_mm_projector")
     for pj in projs:
         specs.append((f"model.{pj}.0.weight", (H, d), "normal", (d ** -0.5)))
         specs.append((f"model.{pj}.0.bias", (H,), "bias", 0.02))
@@ -123,7 +130,8 @@ def weight_specs(g: ModelGeometry):
     specs.append(("model.embed_tokens.weight", (g.llm_vocab, H), "normal", s))
     # vcoder_lm_emb is overwritten with a clone of embed_tokens on every prefill (vcoder_ds_llava_arch.py:173,
     # SURVEY F7): whatever the checkpoint holds is dead.  Generated with different values to prove it is ignored.
-    specs.append(("model.vcoder_lm_emb.weight", (g.llm_vocab, H), "normal", s))
+    if g.variant in (VARIANT_VCODER, VARIANT_VCODER_DS):
+        specs.append(("model.vcoder_lm_emb.weight", (g.llm_vocab, H), "normal", s))
     for i in range(g.llm_layers):
         p = f"model.layers.{i}."
         for n in ("q_proj", "k_proj", "v_proj", "o_proj"):
@@ -175,8 +183,8 @@ def make_prompt_ids(g: ModelGeometry, batch: int, seed: int = 0, n_before: int =
     VCoder-DS `_tokenizer_depth_token` emits [IMAGE, DEPTH, SEG] (mm_utils.py:101-103), VCoder
     `tokenizer_seg_token` emits [IMAGE, SEG]. Text ids are >= 3 so pad/eos/bos never occur."""
     if specials is None:
-        specials = ([IMAGE_TOKEN_INDEX, DEPTH_TOKEN_INDEX, SEG_TOKEN_INDEX] if g.variant == VARIANT_VCODER_DS
-                    else [IMAGE_TOKEN_INDEX, SEG_TOKEN_INDEX])
+        specials = {VARIANT_VCODER_DS: [IMAGE_TOKEN_INDEX, DEPTH_TOKEN_INDEX, SEG_TOKEN_INDEX],
+                    VARIANT_LLAVA: [IMAGE_TOKEN_INDEX]}.get(g.variant, [IMAGE_TOKEN_INDEX, SEG_TOKEN_INDEX])
     gen = torch.Generator().manual_seed(1000 + seed)
     rows = []
     for _ in range(batch):
