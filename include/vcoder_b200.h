@@ -137,6 +137,15 @@ int vcb_op_attention_vit_f16(const vcb_half* qkv_dev, int32_t B, int32_t S, int3
 int vcb_op_sample_f16(const vcb_half* logits_dev, int32_t B, int32_t V, float temperature, int32_t top_k, float top_p,
                       uint64_t seed, int32_t step, int32_t* next_ids_dev, int32_t* kept_dev, void* stream);
 
+/* process_images + CLIPImageProcessor.preprocess for ONE image (vcoder_llava/mm_utils.py:14-40; transformers 4.31
+ * image_processing_clip.py: resize(shortest_edge = out_size, PIL BICUBIC) -> center_crop(out_size) -> rescale(1/255) ->
+ * normalize(mean, std)) followed by the callers' `.to(device, dtype=torch.float16)` (serve/cli.py:74-88).
+ * img_any: uint8 [height, width, 3] RGB, host or device.  pad_rgb: NULL, or the 3 background bytes of expand2square
+ * (`image_aspect_ratio == 'pad'`: tuple(int(x*255) for x in image_mean)).  out_dev: fp16 [3, out_size, out_size].
+ * The resize is bit-exact with Pillow's ImagingResample (integer arithmetic).  Synchronous. */
+int vcb_op_preprocess_u8(const uint8_t* img_any, int32_t height, int32_t width, const uint8_t* pad_rgb, int32_t out_size,
+                         const float* mean3, const float* std3, vcb_half* out_dev, void* stream);
+
 /* ---- host-only logic ------------------------------------------------------------------------ */
 
 /* The splice plan of prepare_inputs_labels_for_multimodal (vcoder_ds_llava_arch.py:175-312 /

@@ -185,6 +185,33 @@ def tokenizer_order_fixture(out_path):
     print(out_path, ds, sg)
 
 
+def preprocess_fixture(out_path):
+    """f2 known answers: the reference's own `process_images` (mm_utils.py:28-40) with and without
+    `image_aspect_ratio='pad'`, driving the PIL-backed CLIP image processor (the algorithm of the pinned transformers 4.31
+    CLIPImageProcessor; 5.5.0 ships it as CLIPImageProcessorPil, its default is a torchvision backend that differs by
+    +-1 LSB from PIL)."""
+    from PIL import Image
+    from transformers.models.clip import CLIPImageProcessorPil
+    rng = np.random.default_rng(5)
+    out = {}
+    for size in (56,):  # 336-pixel outputs are checked against Pillow itself in tests/test_preprocess_host.py
+        ip = CLIPImageProcessorPil(size={"shortest_edge": size}, crop_size={"height": size, "width": size})
+        shapes = [(40, 90), (97, 61), (56, 56), (150, 149)]
+        for k, (h, w) in enumerate(shapes):
+            img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+            # smooth half of them so the resize sees structure, not only noise
+            if k % 2 == 0:
+                yy, xx = np.mgrid[0:h, 0:w]
+                img = np.stack([(yy * 255 // h), (xx * 255 // w), ((yy + xx) * 255 // (h + w))], -1).astype(np.uint8) ^ (img & 7)
+            out[f"img_{size}_{k}"] = img
+            for pad in (False, True):
+                cfg = types.SimpleNamespace(image_aspect_ratio="pad" if pad else None)
+                ref = mm_utils.process_images([Image.fromarray(img)], ip, cfg)[0].numpy()
+                out[f"out_{size}_{k}_{'pad' if pad else 'crop'}"] = ref
+    np.savez_compressed(out_path, **out)
+    print(out_path, sorted(out))
+
+
 if __name__ == "__main__":
     gold = os.path.join(ROOT, "tests", "golden")
     os.makedirs(gold, exist_ok=True)
@@ -194,6 +221,7 @@ if __name__ == "__main__":
         run_variant(synth.PRESETS["tiny"].with_variant(synth.VARIANT_VCODER_DS), os.path.join(gold, "tiny_ds.npz"))
         run_variant(synth.PRESETS["tiny"].with_variant(synth.VARIANT_VCODER), os.path.join(gold, "tiny_vcoder.npz"))
     tokenizer_order_fixture(os.path.join(gold, "tokenizer_order.npz"))
+    preprocess_fixture(os.path.join(gold, "preprocess.npz"))
     # SURVEY §8 f4 variants
     run_variant(synth.PRESETS["tiny"].with_variant(synth.VARIANT_LLAVA), os.path.join(gold, "tiny_llava.npz"))
     run_variant(synth.PRESETS["tiny"].with_variant(synth.VARIANT_VCODER_IT), os.path.join(gold, "tiny_it.npz"))

@@ -70,6 +70,7 @@ SIGNATURES = {
     "vcb_set_sampling": (C.c_int, [_p, _i32, _f, _i32, _f, C.c_uint64, _p]),
     "vcb_decode_stream": (C.c_int, [_p, _i32, _i32, TOKEN_CALLBACK, _p, _p, _p]),
     "vcb_op_sample_f16": (C.c_int, [_p, _i32, _i32, _f, _i32, _f, C.c_uint64, _i32, _p, _p, _p]),
+    "vcb_op_preprocess_u8": (C.c_int, [_p, _i32, _i32, _p, _i32, _p, _p, _p, _p]),
     "vcb_philox_uniform": (C.c_float, [C.c_uint64, C.c_uint32, C.c_uint32]),
     "vcb_bench_weight_stream": (C.c_int, [_p, _i32, _i32, _p, _p, _p]),
     "vcb_reset": (C.c_int, [_p]),

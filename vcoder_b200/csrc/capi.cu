@@ -251,6 +251,12 @@ int vcb_op_sample_f16(const vcb_half* logits, int32_t B, int32_t V, float temper
   return rc;
 }
 
+int vcb_op_preprocess_u8(const uint8_t* img, int32_t height, int32_t width, const uint8_t* pad_rgb, int32_t out_size,
+                         const float* mean3, const float* std3, vcb_half* out, void* stream) {
+  VCB_TRY(require_device());
+  return preprocess_u8(img, height, width, pad_rgb, out_size, mean3, std3, H(out), ST(stream));
+}
+
 float vcb_philox_uniform(uint64_t seed, uint32_t step, uint32_t row) {
   return static_cast<float>(philox_first_host(seed, step, row) >> 8) * (1.0f / 16777216.0f);
 }

@@ -96,6 +96,11 @@ int sample_rows(const __half* logits, int B, int V, const void* params_dev, cons
                 int32_t* next, int32_t* trace, int trace_stride, int32_t* kept_out, cudaStream_t s);
 void pack_sample_params(float temperature, int top_k, float top_p, uint64_t seed, void* out20);
 uint32_t philox_first_host(uint64_t seed, uint32_t step, uint32_t row);
+// process_images (mm_utils.py:28-40) for one uint8 HWC RGB image (host or device) -> fp16 [3,size,size] on the device:
+// optional expand2square with pad_rgb, PIL-exact bicubic resize of the shortest edge to `size`, centre crop, rescale,
+// normalize (preprocess.cu).  Synchronous on `st`.
+int preprocess_u8(const uint8_t* img_any, int height, int width, const uint8_t* pad_rgb, int size, const float* mean,
+                  const float* stdv, __half* out_dev, cudaStream_t st);
 int compact_patches(const __half* hidden, __half* out, int B, int tokens, int D, cudaStream_t s);
 int advance_counters(int32_t* counters, cudaStream_t s);
 void build_rope_table(float2* host_table, int max_pos, int head_dim, float theta);

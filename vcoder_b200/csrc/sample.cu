@@ -12,6 +12,7 @@
 // torch.multinomial's own RNG stream cannot be reproduced (and differs CPU vs CUDA in the reference itself); the draw is
 // the inverse CDF of the filtered distribution at u = Philox4x32-10(seed; step, row), which the oracle restates bit for bit.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.h"
@@ -96,43 +97,106 @@ struct SampleDeviceParams {  // lives in device memory so a captured decode grap
   uint32_t seed_lo, seed_hi;
 };
 
-__global__ void __launch_bounds__(kSampleThreads)
-sample_kernel(const __half* __restrict__ logits, int V, int n_sort, const SampleDeviceParams* __restrict__ prm,
-              const int32_t* __restrict__ step_dev, int step_host, int32_t* next, int32_t* trace, int trace_stride,
-              int32_t* kept_out) {
-  extern __shared__ uint32_t s_w[];  // n_sort packed words
-  __shared__ float s_f[kSampleThreads / 32];
-  __shared__ int s_i[kSampleThreads / 32];
-  __shared__ float s_z2;
-  griddep_launch();
-  griddep_wait();
-  const int b = blockIdx.x, tid = threadIdx.x;
-  const unsigned short* row = reinterpret_cast<const unsigned short*>(logits) + static_cast<long>(b) * V;
-  for (int i = tid; i < n_sort; i += kSampleThreads)
-    s_w[i] = i < V ? ((half_bits_to_key(row[i]) << 16) | (0xFFFFu - static_cast<uint32_t>(i))) : 0u;
-  __syncthreads();
-  // ---- bitonic sort, descending: score desc, index asc among equal scores
-  for (int k = 2; k <= n_sort; k <<= 1) {
+// in-place bitonic sort of n (power of two) words, descending
+__device__ __forceinline__ void bitonic_desc(uint32_t* a, int n) {
+  const int tid = threadIdx.x;
+  for (int k = 2; k <= n; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = tid; t < (n_sort >> 1); t += kSampleThreads) {
+      for (int t = tid; t < (n >> 1); t += kSampleThreads) {
         const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
         const int p = i + j;
-        const uint32_t a = s_w[i], c = s_w[p];
+        const uint32_t x = a[i], y = a[p];
         const bool desc = (i & k) == 0;
-        if (desc ? (a < c) : (a > c)) { s_w[i] = c; s_w[p] = a; }
+        if (desc ? (x < y) : (x > y)) { a[i] = y; a[p] = x; }
       }
       __syncthreads();
     }
   }
+}
+
+constexpr int kCandMax = 2048;  // top-k fast path: survivors (k + ties with the k-th score) sorted on their own
+
+__global__ void __launch_bounds__(kSampleThreads)
+sample_kernel(const __half* __restrict__ logits, int V, int n_sort, const SampleDeviceParams* __restrict__ prm,
+              const int32_t* __restrict__ step_dev, int step_host, int32_t* next, int32_t* trace, int trace_stride,
+              int32_t* kept_out, int allow_select) {
+  extern __shared__ uint32_t s_all[];  // [n_sort] packed row | [kCandMax] top-k survivors
+  __shared__ float s_f[kSampleThreads / 32];
+  __shared__ int s_i[kSampleThreads / 32];
+  __shared__ int s_hist[256];
+  __shared__ int s_sel[4];
+  __shared__ float s_z2;
+  griddep_launch();
+  griddep_wait();
+  const int b = blockIdx.x, tid = threadIdx.x;
+  uint32_t* s_w = s_all;
+  const unsigned short* row = reinterpret_cast<const unsigned short*>(logits) + static_cast<long>(b) * V;
+  for (int i = tid; i < n_sort; i += kSampleThreads)
+    s_w[i] = i < V ? ((half_bits_to_key(row[i]) << 16) | (0xFFFFu - static_cast<uint32_t>(i))) : 0u;
   const float inv_t = prm->inv_temperature, top_p = prm->top_p;
   const int top_k = prm->top_k;
-  // ---- top-k with ties (TopKLogitsWarper removes scores < the k-th largest)
+  __syncthreads();
+
   int n_k = V;
-  if (top_k > 0 && top_k < V) {
-    const uint32_t kth = s_w[top_k - 1] >> 16;
+  bool sorted = false;
+  if (allow_select && top_k > 0 && top_k <= 1024 && top_k < V) {
+    // ---- top-k by two-level radix select on the 16-bit key (integer histograms: exact and deterministic), then only the
+    //      survivors are sorted.  TopKLogitsWarper keeps every score >= the k-th largest, ties included.
+    for (int level = 0; level < 2; ++level) {
+      for (int i = tid; i < 256; i += kSampleThreads) s_hist[i] = 0;
+      __syncthreads();
+      const uint32_t hb = static_cast<uint32_t>(s_sel[0]);
+      for (int i = tid; i < V; i += kSampleThreads) {
+        const uint32_t key = s_w[i] >> 16;
+        if (level == 0) atomicAdd(&s_hist[key >> 8], 1);
+        else if ((key >> 8) == hb) atomicAdd(&s_hist[key & 0xFFu], 1);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int need = level == 0 ? top_k : s_sel[1];  // rank (1-based, from the top) still to find inside this level
+        int bin = 255;
+        for (; bin > 0; --bin) {
+          if (s_hist[bin] >= need) break;
+          need -= s_hist[bin];
+        }
+        if (level == 0) { s_sel[0] = bin; s_sel[1] = need; }
+        else s_sel[2] = (s_sel[0] << 8) | bin;
+      }
+      __syncthreads();
+    }
+    const uint32_t kth = static_cast<uint32_t>(s_sel[2]);
     int c = 0;
-    for (int i = tid; i < n_sort; i += kSampleThreads) c += (i < V && (s_w[i] >> 16) >= kth) ? 1 : 0;
+    for (int i = tid; i < V; i += kSampleThreads) c += ((s_w[i] >> 16) >= kth) ? 1 : 0;
     n_k = block_sum_int(c, s_i);
+    if (n_k <= kCandMax) {
+      uint32_t* cand = s_all + n_sort;
+      int n2 = 32;
+      while (n2 < n_k) n2 <<= 1;
+      if (tid == 0) s_sel[3] = 0;
+      for (int i = tid; i < n2; i += kSampleThreads) cand[i] = 0u;
+      __syncthreads();
+      for (int i = tid; i < V; i += kSampleThreads) {
+        const uint32_t wv = s_w[i];
+        if ((wv >> 16) >= kth) cand[atomicAdd(&s_sel[3], 1)] = wv;  // slot order is arbitrary; the sort below fixes it
+      }
+      __syncthreads();
+      bitonic_desc(cand, n2);
+      s_w = cand;
+      n_sort = n2;
+      sorted = true;
+    }
+  }
+  if (!sorted) {
+    // ---- full bitonic sort, descending: score desc, index asc among equal scores
+    bitonic_desc(s_w, n_sort);
+    // ---- top-k with ties (TopKLogitsWarper removes scores < the k-th largest)
+    n_k = V;
+    if (top_k > 0 && top_k < V) {
+      const uint32_t kth = s_w[top_k - 1] >> 16;
+      int c = 0;
+      for (int i = tid; i < n_sort; i += kSampleThreads) c += (i < V && (s_w[i] >> 16) >= kth) ? 1 : 0;
+      n_k = block_sum_int(c, s_i);
+    }
   }
   // ---- softmax numerators on the sorted row; every thread owns a contiguous chunk so the scan runs in rank order
   const int ept = n_sort / kSampleThreads > 0 ? n_sort / kSampleThreads : 1;
@@ -207,16 +271,19 @@ int sample_rows(const __half* logits, int B, int V, const void* params_dev, cons
   VCB_CHECK(V >= 2 && V <= kSampleMaxV, kErrInvalid, "sampling: vocabulary must be in [2, 32768]");
   int n_sort = kSampleThreads;  // at least one element per thread keeps the chunked scans simple
   while (n_sort < V) n_sort <<= 1;
-  const size_t smem = static_cast<size_t>(n_sort) * 4;
+  const size_t smem = static_cast<size_t>(n_sort + kCandMax) * 4;
   static bool attr_set = false;
   if (!attr_set) {
-    VCB_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSampleMaxV * 4));
+    VCB_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (kSampleMaxV + kCandMax) * 4));
     attr_set = true;
   }
+  static int full_env = -1;  // VCB_SAMPLE_FULLSORT=1: always sort the whole row (A/B against the top-k select path)
+  if (full_env < 0) { const char* ev = getenv("VCB_SAMPLE_FULLSORT"); full_env = ev ? atoi(ev) : 0; }
   KernelScope scope(kCatMisc, s);
   VCB_CUDA(launch_pdl(sample_kernel, dim3(B), dim3(kSampleThreads), smem, s, logits, V, n_sort,
                       static_cast<const SampleDeviceParams*>(params_dev), step_dev, step_host, next, trace,
-                      trace_stride, kept_out));
+                      trace_stride, kept_out, full_env ? 0 : 1));
   return kOk;
 }
 
