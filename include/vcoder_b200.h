@@ -191,6 +191,29 @@ int vcb_prefill(vcb_handle h, const int64_t* ids_host, int32_t B, int32_t T, con
                 const vcb_half* segs_any, const vcb_half* depths_any, int32_t* next_ids_any, vcb_half* last_logits_any,
                 vcb_half* embeds_any, int32_t* spliced_len_host, void* stream);
 
+/* vcb_prefill for multi-turn callers.  serve/chat.py:41-159 (Chat.generate_stream) and the
+ * serve/cli.py:80-135 loop re-tokenise the WHOLE conversation and re-send every image on every turn, and
+ * prepare_inputs_for_generation re-threads images/segs/depths (vcoder_ds_llava_llama.py:137-139), so the reference
+ * re-runs the three towers and re-prefills the 1152 visual tokens per turn.  Same arguments and results as vcb_prefill
+ * (no `embeds` output), but:
+ *   - the pixels are fingerprinted on the device; when they equal the previous call's (same B, same modalities) the
+ *     towers and projectors are skipped (*towers_skipped = 1) and the projected features kept in the handle are used;
+ *   - positions [0, *reused_len) — the longest prefix, common to every sequence of the batch, that the new spliced
+ *     prompt shares with what the KV cache already holds (previous spliced prompt + the generated tokens already fed
+ *     back) — keep their KV entries; only positions [*reused_len, T') run through the decoder.  Visual positions are
+ *     only reused when the features are the same.  The last position always runs.
+ * Row arithmetic is position-wise identical to a full prefill; KV entries of previously GENERATED tokens were produced
+ * by the decode kernels, so logits agree with a full re-prefill to fp16 round-off, not bit for bit. */
+int vcb_prefill_cached(vcb_handle h, const int64_t* ids_host, int32_t B, int32_t T, const vcb_half* images_any,
+                       const vcb_half* segs_any, const vcb_half* depths_any, int32_t* next_ids_any,
+                       vcb_half* last_logits_any, int32_t* spliced_len_host, int32_t* reused_len_host,
+                       int32_t* towers_skipped_host, void* stream);
+
+/* Host-only part of the above: the longest prefix (<= limit) shared by every row of cached [B, cached_len] and
+ * plan [B, plan_len] (vcb_splice_plan entries); visual rows (<= -2) only match when features_same != 0.  Needs no GPU. */
+int vcb_prefix_match(const int32_t* cached_host, int32_t cached_len, const int32_t* plan_host, int32_t plan_len, int32_t B,
+                     int32_t features_same, int32_t limit, int32_t* out_len);
+
 /* n_steps greedy decode steps (prepare_inputs_for_generation + forward + argmax, vcoder_ds_llava_llama.py:120-142;
  * every cached position is attended, padding included: vcoder_ds_llava_arch.py:130-133).  out_ids_any [B,n_steps]
  * int32 receives the tokens produced by THIS call; logits_trace_any [n_steps,B,V] fp16 optional (disables the CUDA

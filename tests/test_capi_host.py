@@ -219,3 +219,53 @@ def test_splice_plan_fuzz_llava_and_it():
         assert got == want, (variant, ids.tolist(), has_seg, nz)
         n_ok += want is not None
     assert n_ok > 50
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# f3: the host half of the multi-turn prefix cache (vcb_prefix_match) against a plain-Python restatement
+# ---------------------------------------------------------------------------------------------------------------
+def _prefix_match_py(cached, plan, features_same, limit):
+    best = min(len(cached[0]), len(plan[0]), limit)
+    for c, p in zip(cached, plan):
+        i = 0
+        while i < best and c[i] == p[i] and (features_same or p[i] > -2):
+            i += 1
+        best = i
+    return max(best, 0)
+
+
+def test_prefix_match_host_cases():
+    from vcoder_b200.engine import prefix_match
+    P = 4
+    plan1 = splice_plan(synth.VARIANT_VCODER_DS, [[1, 5, I, D, S, 9]], P)           # turn 1
+    plan2 = splice_plan(synth.VARIANT_VCODER_DS, [[1, 5, I, D, S, 9, 40, 41, 7]], P)  # turn 2: + answer + question
+    cached = np.concatenate([plan1, np.array([[40]], dtype=np.int32)], axis=1)      # one generated token fed back
+    T1 = plan1.shape[1]
+    assert T1 == 2 + 2 * P + 1
+    assert prefix_match(cached, plan2) == T1 + 1                       # prompt + the fed token
+    assert prefix_match(cached, plan2, features_same=False) == 2      # stops at the first visual row
+    assert prefix_match(cached, plan2, limit=5) == 5
+    assert prefix_match(plan1, plan1, limit=T1 - 1) == T1 - 1         # regenerate: the last position always runs
+    assert prefix_match(plan1[:, :0], plan2) == 0                      # nothing cached
+    # batch: the shortest common prefix wins
+    a = np.array([[1, 2, 3, 4, 5], [1, 2, 3, 4, 5]], dtype=np.int32)
+    b = np.array([[1, 2, 3, 4, 5, 6], [1, 2, 9, 4, 5, 6]], dtype=np.int32)
+    assert prefix_match(a, b) == 2
+    with pytest.raises(ValueError):
+        prefix_match(a, b[:1])
+
+
+def test_prefix_match_host_random():
+    from vcoder_b200.engine import prefix_match
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        B = int(rng.integers(1, 4))
+        lc, lp = int(rng.integers(0, 12)), int(rng.integers(1, 12))
+        base = rng.integers(-6, 5, size=(B, max(lc, lp))).astype(np.int32)
+        cached, plan = base[:, :lc].copy(), base[:, :lp].copy()
+        for b in range(B):  # inject a divergence in some rows
+            if rng.random() < 0.5 and lp > 0:
+                plan[b, int(rng.integers(0, lp))] += 1
+        fs = bool(rng.integers(0, 2))
+        limit = int(rng.integers(0, lp + 2))
+        assert prefix_match(cached, plan, fs, limit) == _prefix_match_py(cached.tolist(), plan.tolist(), fs, limit)

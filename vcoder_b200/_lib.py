@@ -65,6 +65,8 @@ SIGNATURES = {
     "vcb_tower_forward": (C.c_int, [_p, _p, _i32, _p, _p]),
     "vcb_encode": (C.c_int, [_p, _i32, _p, _i32, _p, _p]),
     "vcb_prefill": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "vcb_prefill_cached": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "vcb_prefix_match": (C.c_int, [_p, _i32, _p, _i32, _i32, _i32, _i32, _p]),
     "vcb_decode": (C.c_int, [_p, _i32, _p, _p, _p]),
     "vcb_generate": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _i32, _p, _p]),
     "vcb_set_sampling": (C.c_int, [_p, _i32, _f, _i32, _f, C.c_uint64, _p]),

@@ -69,12 +69,14 @@ attn_prefill_kernel(AttnPrefillParams p) {
   const int g = lane >> 2, t = lane & 3;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int q0 = qt * kBM;
-  const int S = p.seq_len;
+  const int S = p.seq_len;           // query rows per sequence
+  const int P0 = PAGED ? p.q_pos0 : 0;  // position of query row 0: > 0 when a cached prefix is reused (f3)
+  const int KV = P0 + S;             // keys visible to the last query row
 
   const __half* q_base = p.q + (static_cast<long>(b) * S) * p.q_stride + h * DH;
   // number of key tiles this query tile needs
-  int n_tiles = (S + kBN - 1) / kBN;
-  if (CAUSAL) n_tiles = min(n_tiles, (q0 + kBM + kBN - 1) / kBN);
+  int n_tiles = (KV + kBN - 1) / kBN;
+  if (CAUSAL) n_tiles = min(n_tiles, (P0 + q0 + kBM + kBN - 1) / kBN);
 
   auto load_kv = [&](int tile, int buf) {
     const __half* kb;
@@ -95,7 +97,7 @@ attn_prefill_kernel(AttnPrefillParams p) {
     for (int i = 0; i < (kBN * CH) / kAttnThreads; ++i) {
       const int idx = tid + i * kAttnThreads;
       const int r = idx / CH, c = idx % CH;
-      const bool ok = (tile * kBN + r) < S;
+      const bool ok = (tile * kBN + r) < KV;
       const long goff = ok ? (r * stride + c * 8) : 0;
       cp_async16(sK + buf * kTileBytes + tile_off<DH>(r, c), kb + goff, ok);
       cp_async16(sV + buf * kTileBytes + tile_off<DH>(r, c), vb + goff, ok);
@@ -157,7 +159,7 @@ attn_prefill_kernel(AttnPrefillParams p) {
 
     // ---- mask + online softmax (fp32)
     const int key0 = tile * kBN;
-    const bool need_mask = (key0 + kBN > S) || (CAUSAL && (key0 + kBN - 1 > q0 + warp * 16));
+    const bool need_mask = (key0 + kBN > KV) || (CAUSAL && (key0 + kBN - 1 > P0 + q0 + warp * 16));
     float m_new[2] = {m_run[0], m_run[1]};
 #pragma unroll
     for (int j = 0; j < kBN / 8; ++j) {
@@ -167,7 +169,7 @@ attn_prefill_kernel(AttnPrefillParams p) {
         if (need_mask) {
           const int key = key0 + j * 8 + 2 * t + (e & 1);
           const int qr = qrow[e >> 1];
-          if (key >= S || (CAUSAL && key > qr)) v = -INFINITY;
+          if (key >= KV || (CAUSAL && key > P0 + qr)) v = -INFINITY;
         }
         s[j][e] = v;
         m_new[e >> 1] = fmaxf(m_new[e >> 1], v);

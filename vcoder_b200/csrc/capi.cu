@@ -160,6 +160,7 @@ int vcb_tower_forward(vcb_handle h, const vcb_half* pixels, int32_t n, vcb_half*
   VCB_CHECK(n >= 1 && n <= e->vit_max_images, kErrInvalid, "vcb_tower_forward: n must be in [1, 3*max_batch]");
   const size_t img = 3ul * e->cfg.vit_image_size * e->cfg.vit_image_size * 2;
   StreamGuard sg(e, ST(stream));
+  e->feat_key = 0;  // pix / vh are overwritten: the prefix cache must not skip the towers on the next prefill
   VCB_TRY(copy_any(e->pix.p, pixels, n * img, sg.st));
   VCB_TRY(engine_tower(e, e->pix.as<__half>(), n, sg.st));
   // feature_select 'patch': drop CLS; compact into vn then copy out (out may be host memory)
@@ -179,6 +180,7 @@ int vcb_encode(vcb_handle h, int32_t modality, const vcb_half* pixels, int32_t n
   VCB_CHECK(n >= 1 && n <= e->vit_max_images, kErrInvalid, "vcb_encode: n must be in [1, 3*max_batch]");
   const size_t img = 3ul * e->cfg.vit_image_size * e->cfg.vit_image_size * 2;
   StreamGuard sg(e, ST(stream));
+  e->feat_key = 0;  // pix / vh / feats are overwritten
   VCB_TRY(copy_any(e->pix.p, pixels, n * img, sg.st));
   VCB_TRY(engine_tower(e, e->pix.as<__half>(), n, sg.st));
   VCB_TRY(engine_project(e, 0, n * e->S, modality == 0 ? e->mm : e->seg, sg.st));
@@ -192,8 +194,31 @@ int vcb_prefill(vcb_handle h, const int64_t* ids, int32_t B, int32_t T, const vc
   VCB_CHECK(h != nullptr, kErrInvalid, "null handle");
   int len = 0;
   StreamGuard sg(h->e, ST(stream));
-  VCB_TRY(engine_prefill(h->e, ids, B, T, images, segs, depths, next_ids, last_logits, embeds, &len, sg.st));
+  VCB_TRY(engine_prefill(h->e, ids, B, T, images, segs, depths, false, next_ids, last_logits, embeds, &len, nullptr,
+                         nullptr, sg.st));
   if (spliced_len) *spliced_len = len;
+  return kOk;
+}
+
+int vcb_prefill_cached(vcb_handle h, const int64_t* ids, int32_t B, int32_t T, const vcb_half* images,
+                       const vcb_half* segs, const vcb_half* depths, int32_t* next_ids, vcb_half* last_logits,
+                       int32_t* spliced_len, int32_t* reused_len, int32_t* towers_skipped, void* stream) {
+  VCB_CHECK(h != nullptr, kErrInvalid, "null handle");
+  int len = 0, reused = 0, skipped = 0;
+  StreamGuard sg(h->e, ST(stream));
+  VCB_TRY(engine_prefill(h->e, ids, B, T, images, segs, depths, true, next_ids, last_logits, nullptr, &len, &reused,
+                         &skipped, sg.st));
+  if (spliced_len) *spliced_len = len;
+  if (reused_len) *reused_len = reused;
+  if (towers_skipped) *towers_skipped = skipped;
+  return kOk;
+}
+
+int vcb_prefix_match(const int32_t* cached, int32_t cached_len, const int32_t* plan, int32_t plan_len, int32_t B,
+                     int32_t features_same, int32_t limit, int32_t* out_len) {
+  VCB_CHECK(cached != nullptr && plan != nullptr && out_len != nullptr && B >= 1 && cached_len >= 0 && plan_len >= 0,
+            kErrInvalid, "vcb_prefix_match: bad arguments");
+  *out_len = prefix_match_host(cached, cached_len, plan, plan_len, B, features_same, limit);
   return kOk;
 }
 
@@ -209,7 +234,8 @@ int vcb_generate(vcb_handle h, const int64_t* ids, int32_t B, int32_t T, const v
   VCB_CHECK(max_new_tokens >= 1, kErrInvalid, "vcb_generate: max_new_tokens must be >= 1");
   Engine* e = h->e;
   StreamGuard sg(e, ST(stream));
-  VCB_TRY(engine_prefill(e, ids, B, T, images, segs, depths, nullptr, nullptr, nullptr, nullptr, sg.st));
+  VCB_TRY(engine_prefill(e, ids, B, T, images, segs, depths, false, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                         sg.st));
   VCB_TRY(engine_decode(e, max_new_tokens - 1, nullptr, nullptr, sg.st));
   std::vector<int32_t> tmp(static_cast<size_t>(B) * max_new_tokens);
   VCB_CUDA(cudaMemcpy2DAsync(tmp.data(), static_cast<size_t>(max_new_tokens) * 4, e->trace.p,

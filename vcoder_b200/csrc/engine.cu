@@ -73,6 +73,7 @@ Engine::~Engine() {
   if (plan_host) cudaFreeHost(plan_host);
   if (bt_host) cudaFreeHost(bt_host);
   if (depth_host) cudaFreeHost(depth_host);
+  if (fp_host) cudaFreeHost(fp_host);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -171,11 +172,13 @@ int engine_create(const vcb_config* c, int device, Engine** out) {
   if (rc == kOk) rc = dev_alloc(e, &e->rope, static_cast<size_t>(c->max_seq_len) * 64 * sizeof(float2));
   if (rc == kOk) rc = dev_alloc(e, &e->counters, 16);
   if (rc == kOk) rc = dev_alloc(e, &e->sample_params, 32);
+  if (rc == kOk) rc = dev_alloc(e, &e->fp_dev, 8);
 #undef ALLOC
   if (rc != kOk) { delete e; return rc; }
   if (cudaMallocHost(&e->plan_host, e->max_rows * 4) != cudaSuccess ||
       cudaMallocHost(&e->bt_host, static_cast<size_t>(B) * e->max_pages_per_seq * 4) != cudaSuccess ||
       cudaMallocHost(&e->depth_host, B * 4) != cudaSuccess ||
+      cudaMallocHost(&e->fp_host, 8) != cudaSuccess ||
       cudaMallocHost(&e->stream_host, static_cast<size_t>(Engine::kStreamRing) * B * 4) != cudaSuccess) {
     delete e;
     set_thread_error("cudaMallocHost failed");
@@ -551,6 +554,22 @@ __global__ void depth_sum_kernel(const __half* px, long per_image, float* sums) 
   if ((threadIdx.x & 31) == 0) atomicAdd(sums + b, s);
 }
 
+// f3: order-independent 64-bit fingerprint of a pixel buffer (sum of position-keyed splitmix64 hashes of its 8-byte
+// words): identifies "the same images as the previous turn" without a host copy of the pixels
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z ^= z >> 30; z *= 0xbf58476d1ce4e5b9ULL;
+  z ^= z >> 27; z *= 0x94d049bb133111ebULL;
+  return z ^ (z >> 31);
+}
+__global__ void fingerprint_kernel(const uint64_t* __restrict__ p, long n_words, unsigned long long* out) {
+  unsigned long long acc = 0;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_words;
+       i += static_cast<long>(gridDim.x) * blockDim.x)
+    acc += mix64(p[i] ^ (0x9e3779b97f4a7c15ULL * static_cast<uint64_t>(i + 1)));
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc != 0) atomicAdd(out, acc);
+}
+
 int ensure_pages(Engine* e, int B, int total_tokens, cudaStream_t st) {
   const int PT = e->cfg.kv_page_tokens;
   const int need = (total_tokens + PT - 1) / PT;
@@ -567,9 +586,22 @@ int ensure_pages(Engine* e, int B, int total_tokens, cudaStream_t st) {
 
 }  // namespace
 
+int prefix_match_host(const int32_t* cached, int cached_len, const int32_t* plan, int plan_len, int B, int features_same,
+                      int limit) {
+  int best = std::min(std::min(cached_len, plan_len), limit);
+  for (int b = 0; b < B && best > 0; ++b) {
+    const int32_t* c = cached + static_cast<long>(b) * cached_len;
+    const int32_t* n = plan + static_cast<long>(b) * plan_len;
+    int i = 0;
+    while (i < best && c[i] == n[i] && (features_same || n[i] > -2)) ++i;
+    best = i;
+  }
+  return std::max(best, 0);
+}
+
 int engine_prefill(Engine* e, const int64_t* ids, int B, int T, const void* images, const void* segs,
-                   const void* depths, void* next_ids_out, void* last_logits_out, void* embeds_out, int* spliced_len,
-                   cudaStream_t st) {
+                   const void* depths, bool reuse, void* next_ids_out, void* last_logits_out, void* embeds_out,
+                   int* spliced_len, int* reused_len, int* towers_skipped, cudaStream_t st) {
   const vcb_config& c = e->cfg;
   VCB_CHECK(ids != nullptr && B >= 1 && B <= c.max_batch && T >= 1, kErrInvalid, "vcb_prefill: bad ids / batch");
   VCB_CUDA(cudaSetDevice(e->device));
@@ -578,13 +610,36 @@ int engine_prefill(Engine* e, const int64_t* ids, int B, int T, const void* imag
   VCB_TRY(engine_check_bound(e, multimodal, true));
   VCB_CHECK(ds || depths == nullptr, kErrInvalid, "only VCoder-DS takes depth images");
   VCB_CHECK(c.variant != VCB_VARIANT_LLAVA || segs == nullptr, kErrInvalid, "LLaVA takes no seg images");
-  const int D = c.vit_hidden, H = c.llm_hidden, FF = c.llm_ffn, V = c.llm_vocab, S = e->S;
+  const int H = c.llm_hidden, FF = c.llm_ffn, V = c.llm_vocab, S = e->S;
   const long img_halves = 3L * c.vit_image_size * c.vit_image_size;
+  if (reused_len) *reused_len = 0;
+  if (towers_skipped) *towers_skipped = 0;
+
+  // ---- f3: what the KV cache holds right now = the previous prompt's plan + the generated tokens already fed back
+  //      (token i of the trace was consumed by decode step i+1, so the last generated token is not cached yet)
+  std::vector<int32_t> cached;
+  int cached_len = 0;
+  if (reuse && e->prefilled && e->batch == B && e->seq_plan_len > 0 && embeds_out == nullptr) {
+    const int fed = e->steps_done - 1;
+    cached_len = e->seq_plan_len + fed;
+    cached.resize(static_cast<size_t>(B) * cached_len);
+    std::vector<int32_t> gen(static_cast<size_t>(B) * std::max(fed, 1));
+    if (fed > 0) {
+      VCB_CUDA(cudaMemcpy2DAsync(gen.data(), static_cast<size_t>(fed) * 4, e->trace.p, static_cast<size_t>(c.max_seq_len) * 4,
+                                 static_cast<size_t>(fed) * 4, B, cudaMemcpyDeviceToHost, st));
+      VCB_CUDA(cudaStreamSynchronize(st));
+    }
+    for (int b = 0; b < B; ++b) {
+      int32_t* dst = cached.data() + static_cast<long>(b) * cached_len;
+      std::memcpy(dst, e->seq_plan.data() + static_cast<long>(b) * e->seq_plan_len, static_cast<size_t>(e->seq_plan_len) * 4);
+      if (fed > 0) std::memcpy(dst + e->seq_plan_len, gen.data() + static_cast<long>(b) * fed, static_cast<size_t>(fed) * 4);
+    }
+  }
   e->prefilled = false;
-  e->pages_per_seq_alloc = 0;
 
   int Tp = T;
   std::vector<int32_t> plan;
+  bool features_same = false;
   if (multimodal) {
     // ---- all modalities in one tower batch: [rgb | seg | depth]
     const int kinds = 1 + (segs ? 1 : 0) + ((ds && depths) ? 1 : 0);
@@ -593,9 +648,30 @@ int engine_prefill(Engine* e, const int64_t* ids, int B, int T, const void* imag
     VCB_TRY(copy_any(pix, images, static_cast<size_t>(B) * img_halves * 2, st));
     if (segs) VCB_TRY(copy_any(pix + B * img_halves, segs, static_cast<size_t>(B) * img_halves * 2, st));
     if (ds && depths) VCB_TRY(copy_any(pix + 2L * B * img_halves, depths, static_cast<size_t>(B) * img_halves * 2, st));
-    VCB_TRY(engine_tower(e, pix, kinds * B, st));
-    VCB_TRY(engine_project(e, 0, B * S, e->mm, st));                // encode_images: mm_projector
-    VCB_TRY(engine_project(e, B * S, kinds * B * S, e->seg, st));   // seg AND depth: seg_mm_projector (F3)
+    uint64_t key = 0;
+    const size_t pix_bytes = static_cast<size_t>(kinds) * B * img_halves * 2;
+    if (reuse && pix_bytes % 8 == 0) {
+      VCB_CUDA(cudaMemsetAsync(e->fp_dev.p, 0, 8, st));
+      fingerprint_kernel<<<4 * device_sm_count(), 256, 0, st>>>(e->pix.as<uint64_t>(), static_cast<long>(pix_bytes / 8),
+                                                                e->fp_dev.as<unsigned long long>());
+      VCB_CUDA(cudaGetLastError());
+      VCB_TRY(copy_any(e->fp_host, e->fp_dev.p, 8, st));
+      VCB_CUDA(cudaStreamSynchronize(st));
+      key = *e->fp_host ^ (0x51ed270b27b4f3cfULL * static_cast<uint64_t>(kinds * 64 + B));
+      if (key == 0) key = 1;
+    }
+    features_same = key != 0 && key == e->feat_key && e->feat_batch == B && e->feat_kinds == kinds;
+    if (!features_same) {
+      e->feat_key = 0;  // `feats` is about to be overwritten
+      VCB_TRY(engine_tower(e, pix, kinds * B, st));
+      VCB_TRY(engine_project(e, 0, B * S, e->mm, st));                // encode_images: mm_projector
+      VCB_TRY(engine_project(e, B * S, kinds * B * S, e->seg, st));   // seg AND depth: seg_mm_projector (F3)
+      e->feat_key = key;
+      e->feat_batch = B;
+      e->feat_kinds = kinds;
+    } else if (towers_skipped) {
+      *towers_skipped = 1;
+    }
     // ---- splice plan; the is_depth_zero (DS) / is_seg_zero (IT) flags cost one host sync, paid only when the plan can
     //      depend on them (DS: a <depth> token is reachable after the seg splice; IT: seg images were passed)
     const bool it = c.variant == VCB_VARIANT_VCODER_IT;
@@ -628,14 +704,22 @@ int engine_prefill(Engine* e, const int64_t* ids, int B, int T, const void* imag
   for (int32_t v : plan) VCB_CHECK(v < V, kErrSpecialIndex, "token id out of range for the embedding table");
   VCB_CHECK(Tp >= 1 && Tp <= c.max_seq_len, kErrNoMem, "spliced prompt exceeds max_seq_len");
   if (spliced_len) *spliced_len = Tp;
-  const long rows = static_cast<long>(B) * Tp;
-  std::memcpy(e->plan_host, plan.data(), rows * 4);
+
+  // ---- f3: positions [0, L0) keep their KV entries; rows [L0, Tp) of every sequence run through the decoder.  The last
+  //      position always runs (its hidden state feeds lm_head)
+  const int L0 = cached_len > 0 ? prefix_match_host(cached.data(), cached_len, plan.data(), Tp, B, features_same ? 1 : 0, Tp - 1) : 0;
+  if (reused_len) *reused_len = L0;
+  const int Ts = Tp - L0;
+  const long rows = static_cast<long>(B) * Ts;
+  for (int b = 0; b < B; ++b)
+    std::memcpy(e->plan_host + static_cast<long>(b) * Ts, plan.data() + static_cast<long>(b) * Tp + L0, static_cast<size_t>(Ts) * 4);
   VCB_TRY(copy_any(e->plan_dev.p, e->plan_host, rows * 4, st));
   __half* x = e->x.as<__half>();
   VCB_TRY(splice_gather(e->plan_dev.as<int32_t>(), e->embed.as<__half>(), e->feats.as<__half>(), x, rows, H, st));
   if (embeds_out) VCB_TRY(copy_any(embeds_out, x, rows * H * 2, st));
 
-  // ---- KV pages for the prompt
+  // ---- KV pages for the prompt (the page ids of a sequence never change, so a reused prefix stays where it is)
+  if (L0 == 0) e->pages_per_seq_alloc = 0;
   VCB_TRY(ensure_pages(e, B, Tp, st));
   const size_t layer_pool = static_cast<size_t>(e->n_pages) * c.llm_heads * c.kv_page_tokens * 128;
   __half* xn = e->xn.as<__half>();
@@ -650,7 +734,7 @@ int engine_prefill(Engine* e, const int64_t* ids, int B, int T, const void* imag
       ep.C = qkv; ep.ldc = 3 * H;
       VCB_TRY(gemm_f16(xn, H, l.qkv_w.as<__half>(), H, rows, 3 * H, H, ep, 0, st));
     }
-    VCB_TRY(rope_kv_write(qkv, B, Tp, H, c.llm_heads, e->rope.as<float2>(), 0, nullptr, kp, vp,
+    VCB_TRY(rope_kv_write(qkv, B, Ts, H, c.llm_heads, e->rope.as<float2>(), L0, nullptr, kp, vp,
                           e->block_table.as<int32_t>(), e->max_pages_per_seq, c.kv_page_tokens, st));
     {
       AttnPrefillParams a;
@@ -658,7 +742,7 @@ int engine_prefill(Engine* e, const int64_t* ids, int B, int T, const void* imag
       a.k_pool = kp; a.v_pool = vp; a.block_table = e->block_table.as<int32_t>();
       a.max_pages = e->max_pages_per_seq; a.page_tokens = c.kv_page_tokens;
       a.out = e->attn.as<__half>(); a.out_stride = H;
-      a.batch = B; a.n_heads = c.llm_heads; a.seq_len = Tp; a.head_dim = 128;
+      a.batch = B; a.n_heads = c.llm_heads; a.seq_len = Ts; a.q_pos0 = L0; a.head_dim = 128;
       a.scale = 0.08838834764831845f;  // 1/sqrt(128)
       VCB_TRY(attn_llama_prefill(a, st));
     }
@@ -681,7 +765,7 @@ int engine_prefill(Engine* e, const int64_t* ids, int B, int T, const void* imag
   }
   // ---- logits for the LAST position only (the reference computes all T' rows and greedy reads [:, -1])
   __half* xd = e->xd.as<__half>();
-  VCB_CUDA(cudaMemcpy2DAsync(xd, H * 2, x + static_cast<long>(Tp - 1) * H, static_cast<size_t>(Tp) * H * 2, H * 2, B,
+  VCB_CUDA(cudaMemcpy2DAsync(xd, H * 2, x + static_cast<long>(Ts - 1) * H, static_cast<size_t>(Ts) * H * 2, H * 2, B,
                              cudaMemcpyDeviceToDevice, st));
   {
     SkinnyParams s;  // final RMSNorm fused into the lm_head GEMM
@@ -698,6 +782,8 @@ int engine_prefill(Engine* e, const int64_t* ids, int B, int T, const void* imag
   VCB_CUDA(cudaMemcpyAsync(counters, after, 12, cudaMemcpyHostToDevice, st));
   if (last_logits_out) VCB_TRY(copy_any(last_logits_out, e->logits.p, static_cast<size_t>(B) * V * 2, st));
   if (next_ids_out) VCB_TRY(copy_any(next_ids_out, e->next_ids.p, B * 4, st));
+  e->seq_plan.swap(plan);
+  e->seq_plan_len = Tp;
   e->batch = B;
   e->cache_len = Tp;
   e->steps_done = 1;
@@ -1002,6 +1088,9 @@ int engine_bench_weight_stream(Engine* e, int B, int rounds, float* ms_total, in
 
 int engine_reset(Engine* e) {
   e->prefilled = false;
+  e->seq_plan.clear();
+  e->seq_plan_len = 0;
+  e->feat_key = 0;
   e->batch = 0;
   e->cache_len = 0;
   e->steps_done = 0;

@@ -83,6 +83,13 @@ struct Engine {
   static constexpr int kStreamRing = 16;
   cudaEvent_t stream_ev[kStreamRing] = {};
   int32_t* stream_host = nullptr;  // pinned [kStreamRing][max_batch]
+  // f3: multi-turn prefix cache (serve/chat.py:41-159 re-sends the whole conversation and all images every turn)
+  std::vector<int32_t> seq_plan;  // host mirror of the last prefill's spliced plan [batch][seq_plan_len]
+  int seq_plan_len = 0;
+  uint64_t feat_key = 0;          // fingerprint of the pixels whose projected features sit in `feats` (0 = none)
+  int feat_batch = 0, feat_kinds = 0;
+  DevBuf fp_dev;                  // 8-byte accumulator of fingerprint_kernel
+  uint64_t* fp_host = nullptr;    // pinned
 
   ~Engine();
 };
@@ -93,9 +100,16 @@ int engine_check_bound(Engine* e, bool need_vision, bool need_llm);
 // images: device pointer to n images [n,3,S,S] fp16 already resident; result rows in e->vh ([n*S, D])
 int engine_tower(Engine* e, const __half* pixels_dev, int n_images, cudaStream_t st);
 int engine_project(Engine* e, int row_begin, int row_end, const ProjW& w, cudaStream_t st);
+// reuse = false: every call runs the towers and the whole prompt (vcb_prefill).  reuse = true (vcb_prefill_cached): the
+// towers are skipped when the pixels' fingerprint equals the previous call's, and only the part of the spliced prompt
+// behind the longest prefix it shares with the sequence already in the KV cache runs through the decoder.
 int engine_prefill(Engine* e, const int64_t* ids_host, int B, int T, const void* images, const void* segs,
-                   const void* depths, void* next_ids_out, void* last_logits_out, void* embeds_out, int* spliced_len,
-                   cudaStream_t st);
+                   const void* depths, bool reuse, void* next_ids_out, void* last_logits_out, void* embeds_out,
+                   int* spliced_len, int* reused_len, int* towers_skipped, cudaStream_t st);
+// Host-only part of the prefix cache: longest prefix (<= limit) shared by every row of `cached` [B][cached_len] and
+// `plan` [B][plan_len]; visual rows (entries <= -2) only count when `features_same`.
+int prefix_match_host(const int32_t* cached, int cached_len, const int32_t* plan, int plan_len, int B, int features_same,
+                      int limit);
 int engine_decode(Engine* e, int n_steps, void* out_ids, void* logits_trace, cudaStream_t st);
 int engine_reset(Engine* e);
 // do_sample / temperature / top_k / top_p / seed of the following prefill + decode calls (HF GenerationMixin.sample)

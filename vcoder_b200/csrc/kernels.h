@@ -21,6 +21,9 @@ struct AttnPrefillParams {
   __half* out = nullptr;  // [B*S, heads*head_dim]
   long out_stride = 0;
   int batch = 0, n_heads = 0, seq_len = 0, head_dim = 0;
+  // paged causal path only: query row i of a sequence sits at position q_pos0 + i and attends to cached keys
+  // [0, q_pos0 + i]; seq_len counts the query rows (f3: prefill of a suffix behind a reused KV prefix)
+  int q_pos0 = 0;
   float scale = 1.f;
 };
 int attn_vit(const AttnPrefillParams& p, cudaStream_t stream);       // dispatcher: tcgen05 kernel when it applies

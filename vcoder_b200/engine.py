@@ -101,7 +101,13 @@ class Engine:
             _lib.check(self.lib.vcb_encode(self.h, modality, _lib.ptr(px), n, _lib.ptr(out), _stream_ptr()))
         return out
 
-    def prefill(self, ids: torch.Tensor, images=None, segs=None, depths=None, want_logits=False, want_embeds=False):
+    def prefill(self, ids: torch.Tensor, images=None, segs=None, depths=None, want_logits=False, want_embeds=False,
+                reuse: bool = False):
+        """vcb_prefill, or with `reuse=True` vcb_prefill_cached (f3): towers skipped when the pixels equal the previous
+        call's, and only the suffix behind the prefix shared with the cached sequence runs through the decoder; the
+        result then also carries `reused_len` and `towers_skipped`."""
+        if reuse and want_embeds:
+            raise ValueError("want_embeds needs the full prompt: not available with reuse=True")
         ids_h = ids.detach().to("cpu", torch.int64).contiguous()
         B, T = ids_h.shape
         self._last_batch = B
@@ -111,12 +117,18 @@ class Engine:
         n_vis = 3 * self.g.n_patches
         embeds = (torch.empty(B, T + n_vis, self.g.llm_hidden, dtype=torch.float16, device=self.tdev)
                   if want_embeds else None)
-        slen = C.c_int32(0)
+        slen, reused, skipped = C.c_int32(0), C.c_int32(0), C.c_int32(0)
         with self.lock:
-            _lib.check(self.lib.vcb_prefill(self.h, _lib.ptr(ids_h), B, T, _lib.ptr(im), _lib.ptr(sg), _lib.ptr(dp),
-                                            _lib.ptr(nxt), _lib.ptr(logits), _lib.ptr(embeds), C.byref(slen),
-                                            _stream_ptr()))
-        out = {"next_ids": nxt, "spliced_len": slen.value}
+            if reuse:
+                _lib.check(self.lib.vcb_prefill_cached(self.h, _lib.ptr(ids_h), B, T, _lib.ptr(im), _lib.ptr(sg),
+                                                       _lib.ptr(dp), _lib.ptr(nxt), _lib.ptr(logits), C.byref(slen),
+                                                       C.byref(reused), C.byref(skipped), _stream_ptr()))
+            else:
+                _lib.check(self.lib.vcb_prefill(self.h, _lib.ptr(ids_h), B, T, _lib.ptr(im), _lib.ptr(sg), _lib.ptr(dp),
+                                                _lib.ptr(nxt), _lib.ptr(logits), _lib.ptr(embeds), C.byref(slen),
+                                                _stream_ptr()))
+        out = {"next_ids": nxt, "spliced_len": slen.value, "reused_len": reused.value,
+               "towers_skipped": bool(skipped.value)}
         if want_logits:
             out["logits"] = logits
         if want_embeds:
@@ -190,6 +202,20 @@ class Engine:
 
     def _batch(self) -> int:
         return getattr(self, "_last_batch", None) or 0
+
+
+def prefix_match(cached, plan, features_same: bool = True, limit: Optional[int] = None) -> int:
+    """Host-only: vcb_prefix_match on two [B, len] int32 arrays of vcb_splice_plan entries (no GPU needed)."""
+    lib = _lib.load()
+    c = np.ascontiguousarray(np.asarray(cached, dtype=np.int32))
+    p = np.ascontiguousarray(np.asarray(plan, dtype=np.int32))
+    if c.ndim != 2 or p.ndim != 2 or c.shape[0] != p.shape[0]:
+        raise ValueError("prefix_match: cached and plan must be [B, len] with the same B")
+    out = C.c_int32(0)
+    lim = p.shape[1] if limit is None else int(limit)
+    _lib.check(lib.vcb_prefix_match(_lib.ptr(c), c.shape[1], _lib.ptr(p), p.shape[1], c.shape[0], int(features_same),
+                                    lim, C.byref(out)))
+    return out.value
 
 
 def splice_plan(variant: int, ids, n_patches: int, has_seg: bool = True, depth_nonzero=None):

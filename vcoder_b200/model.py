@@ -90,6 +90,11 @@ class _VCoderBase:
         # eos/pad come from the checkpoint (builder.load_pretrained_model fills them in), None = never stop early
         self.generation_config = types.SimpleNamespace(eos_token_id=None, pad_token_id=None, top_k=50)
         self.stream_lookahead = 4  # decode steps kept queued on the GPU while Python handles a token
+        # f3: interactive callers (serve/cli.py loop, serve/chat.py:41-159) re-send the whole conversation and every image
+        # each turn; with the prefix cache the towers are skipped for unchanged pixels and only the new part of the prompt
+        # is prefilled.  `last_prefill` reports what the most recent interactive generate() reused.
+        self.prefix_cache = True
+        self.last_prefill = {"spliced_len": 0, "reused_len": 0, "towers_skipped": False}
         if state_dict is not None:
             self.load_state_dict(state_dict)
 
@@ -212,7 +217,8 @@ class _VCoderBase:
                     done = True
                 return done
 
-            pre = self._eng.prefill(input_ids, images, segs, depths)
+            pre = self._eng.prefill(input_ids, images, segs, depths, reuse=self.prefix_cache)
+            self.last_prefill = {k: pre[k] for k in ("spliced_len", "reused_len", "towers_skipped")}
             stop = on_token(0, pre["next_ids"].cpu().tolist())
             if not stop and max_new_tokens > 1:
                 self._eng.decode_stream(max_new_tokens - 1, on_token, lookahead=self.stream_lookahead)
