@@ -375,7 +375,7 @@ def run_b200(args):
                "note": "attention: 4,726,784 algorithmic bytes and 1.364 GFLOP per (image, layer) (SURVEY 8d), per-launch events"}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_sample_tokens_per_s(B, N, repeats=6)
+        cpu = cpu_sample_tokens_per_s(B, N, repeats=20)  # ~15 s of CPU work on the GPU box
     if rank == 0:
         h2d = sum(p.numel() * 2 for p in host_px) + ids.numel() * 8
         line = {

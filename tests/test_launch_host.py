@@ -173,6 +173,13 @@ def test_install_swaps_the_one_name_the_callers_import(rig):
     assert cli.load_pretrained_model.__module__ == "vcoder_llava.model.builder"
     with pytest.raises(FileNotFoundError):
         rig.launch.install(rig.tmp)  # not a VCoder checkout
+    # f2 opt-in: mm_utils.process_images -> the GPU version, in the callers that imported it by name as well
+    from vcoder_b200 import preprocess as b200_pre
+    rig.launch.install(REFERENCE, gpu_preprocess=True)
+    import vcoder_llava.mm_utils as mm
+    assert mm.process_images is b200_pre.process_images and cli.process_images is b200_pre.process_images
+    rig.launch.uninstall()
+    assert cli.process_images.__module__ == "vcoder_llava.mm_utils" and mm.process_images.__module__ == "vcoder_llava.mm_utils"
 
 
 def test_reference_cli_runs_unmodified(rig, monkeypatch, capsys):

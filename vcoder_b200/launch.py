@@ -2,6 +2,7 @@
 
     python -m vcoder_b200.launch [--reference /path/to/VCoder] vcoder_llava.serve.cli --model-path ... --image-file ...
     python -m vcoder_b200.launch [--reference /path/to/VCoder] vcoder_llava.eval.model_depth_loader --model-path ...
+    python -m vcoder_b200.launch --gpu-preprocess vcoder_llava.serve.cli ...     (also swaps mm_utils.process_images)
 
 The reference has no plugin interface: its callers reach the hot path through
 `load_pretrained_model(...)` (vcoder_llava/model/builder.py:25-154) and `model.generate(input_ids, images=, segs=,
@@ -56,11 +57,15 @@ def _stub_missing(name: str) -> None:
         sys.modules[name] = types.ModuleType(name)
 
 
-def install(reference_path: Optional[str] = None):
+def install(reference_path: Optional[str] = None, gpu_preprocess: bool = False):
     """Make `vcoder_llava`'s callers load the B200 model.  Returns the patched `vcoder_llava.model.builder` module.
 
     reference_path: checkout of SHI-Labs/VCoder to put on sys.path (default: $VCODER_REFERENCE, else `vcoder_llava`
-    must already be importable)."""
+    must already be importable).
+    gpu_preprocess: also swap `vcoder_llava.mm_utils.process_images` (mm_utils.py:28-40) for the bit-exact GPU version
+    (`vcoder_b200.preprocess.process_images`).  Off by default: the eval loaders call process_images inside
+    forked DataLoader workers (eval/model_depth_loader.py:75-84), where CUDA cannot be initialised; the single-process
+    callers (serve/cli.py, serve/chat.py) can take it."""
     global _installed
     reference_path = reference_path or os.environ.get("VCODER_REFERENCE")
     if reference_path:
@@ -87,6 +92,16 @@ def install(reference_path: Optional[str] = None):
         if getattr(mod, "load_pretrained_model", None) is getattr(ref_builder, "_reference_load_pretrained_model", None):
             mod.load_pretrained_model = b200_builder.load_pretrained_model
     _installed = True
+    if gpu_preprocess:
+        from . import preprocess as b200_pre
+        ref_mm = importlib.import_module("vcoder_llava.mm_utils")
+        if not hasattr(ref_mm, "_reference_process_images"):
+            ref_mm._reference_process_images = ref_mm.process_images
+        ref_mm.process_images = b200_pre.process_images
+        for mod in list(sys.modules.values()):
+            if mod is not None and mod is not ref_mm and getattr(mod, "__name__", "").startswith("vcoder_llava") and \
+                    getattr(mod, "process_images", None) is ref_mm._reference_process_images:
+                mod.process_images = b200_pre.process_images
     return ref_builder
 
 
@@ -102,22 +117,35 @@ def uninstall() -> None:
             if mod is not None and getattr(mod, "__name__", "").startswith("vcoder_llava") and \
                     getattr(mod, "load_pretrained_model", None) is b200_builder.load_pretrained_model:
                 mod.load_pretrained_model = orig
+    ref_mm = sys.modules.get("vcoder_llava.mm_utils")
+    if ref_mm is not None and hasattr(ref_mm, "_reference_process_images"):
+        from . import preprocess as b200_pre
+        orig_pi = ref_mm._reference_process_images
+        for mod in list(sys.modules.values()):
+            if mod is not None and getattr(mod, "__name__", "").startswith("vcoder_llava") and \
+                    getattr(mod, "process_images", None) is b200_pre.process_images:
+                mod.process_images = orig_pi
     _installed = False
 
 
 def main(argv: Optional[List[str]] = None) -> None:
     argv = list(sys.argv[1:] if argv is None else argv)
-    reference = None
-    if argv and argv[0] == "--reference":
-        if len(argv) < 2:
-            raise SystemExit("--reference needs a path")
-        reference, argv = argv[1], argv[2:]
-    elif argv and argv[0].startswith("--reference="):
-        reference, argv = argv[0].split("=", 1)[1], argv[1:]
+    reference, gpu_preprocess = None, False
+    while argv and argv[0].startswith("--"):
+        if argv[0] == "--reference":
+            if len(argv) < 2:
+                raise SystemExit("--reference needs a path")
+            reference, argv = argv[1], argv[2:]
+        elif argv[0].startswith("--reference="):
+            reference, argv = argv[0].split("=", 1)[1], argv[1:]
+        elif argv[0] == "--gpu-preprocess":
+            gpu_preprocess, argv = True, argv[1:]
+        else:
+            break
     if not argv or argv[0].startswith("-"):
         raise SystemExit(__doc__)
     target = argv[0]
-    install(reference)
+    install(reference, gpu_preprocess=gpu_preprocess)
     sys.argv = [target] + argv[1:]
     runpy.run_module(target, run_name="__main__", alter_sys=True)
 
