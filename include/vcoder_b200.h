@@ -109,6 +109,17 @@ int vcb_op_skinny_gemm_f16(const vcb_half* X_dev, int32_t ldx, const vcb_half* W
                            const vcb_half* residual_dev, int32_t ldr, int32_t swiglu, vcb_half* Y_dev, int32_t ldy,
                            void* stream);
 
+/* The decode weight stream's own HBM layout.  vcb_op_pack_skinny_weights copies a row-major W[N,K] (N % 16 == 0,
+ * K % 64 == 0) into the tile-major form [N/16][K/64][16 rows][128 B] (16-byte chunks pre-swizzled with row & 7), i.e. the
+ * shared-memory image of every 16-row x 64-k block, so that a CTA's 16 x K slab is one contiguous run and a pipeline stage
+ * is one linear 8 KiB bulk copy.  vcb_op_skinny_gemm_packed_f16 is vcb_op_skinny_gemm_f16 reading that copy; same
+ * arithmetic in the same order, hence bit-identical results.  The engine keeps such a copy of every matrix the decode step
+ * streams when VCB_SKINNY_PACKED=1 (replaces the same nn.Linear calls as vcb_op_skinny_gemm_f16). */
+int vcb_op_pack_skinny_weights(const vcb_half* W_dev, int32_t N, int32_t K, vcb_half* Wp_dev, void* stream);
+int vcb_op_skinny_gemm_packed_f16(const vcb_half* X_dev, int32_t ldx, const vcb_half* Wp_dev, int32_t B, int32_t N, int32_t K,
+                                  const vcb_half* residual_dev, int32_t ldr, int32_t swiglu, vcb_half* Y_dev, int32_t ldy,
+                                  void* stream);
+
 /* Same kernel with LlamaRMSNorm fused onto X (decode path): Y = rsqrt(mean(x^2)+eps) * ((x o norm_w) · W^T) (+ residual).
  * Replaces `self.input_layernorm` / `post_attention_layernorm` / `model.norm` followed by the Linear
  * (transformers/models/llama/modeling_llama.py:53-70, 171-184). */

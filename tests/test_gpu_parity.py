@@ -309,3 +309,62 @@ def test_llama_real_width(name, hidden, heads, ffn, layers, batch):
     assert bool(alive.any())
     gen = eng.generate(ids, images, segs, depths, max_new_tokens=n_new)  # CUDA-graph path
     assert torch.equal(gen, got_ids.cpu().long())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# decode weight stream from the tile-major (packed) weight copy: same arithmetic in the same order => bit-identical
+# ---------------------------------------------------------------------------------------------------------------
+def _pack_numpy(W):
+    """[N,K] -> [N/16][K/64][16][8 chunks of 8 halves], chunk position = ch ^ (r & 7) (include/vcoder_b200.h)."""
+    N, K = W.shape
+    w = W.reshape(N // 16, 16, K // 64, 8, 8).transpose(0, 2, 1, 3, 4).copy()  # [tile][kb][r][ch][8]
+    out = np.empty_like(w)
+    for r in range(16):
+        for ch in range(8):
+            out[:, :, r, ch ^ (r & 7)] = w[:, :, r, ch]
+    return out.reshape(-1)
+
+
+@pytest.mark.parametrize("B,N,K,sw,res", [(8, 4096, 4096, 0, 1), (8, 1024, 512, 1, 0), (3, 512, 384, 0, 0), (5, 256, 192, 0, 1),
+                                          (1, 32000, 4096, 0, 0), (16, 2048, 1024, 0, 1), (32, 1024, 512, 1, 0),
+                                          (8, 4096, 11008, 0, 1), (8, 64, 64, 0, 0)])
+def test_skinny_gemm_packed_bit_identical(B, N, K, sw, res):
+    lib = _lib.load()
+    torch.manual_seed(B + N + K)
+    X = (torch.randn(B, K, device=DEV) * 0.5).half()
+    W = (torch.randn(N, K, device=DEV) * 0.03).half()
+    R = torch.randn(B, N, device=DEV).half() if res else None
+    Wp = torch.full((N * K,), float("nan"), device=DEV, dtype=torch.float16)
+    _lib.check(lib.vcb_op_pack_skinny_weights(_lib.ptr(W), N, K, _lib.ptr(Wp), ST))
+    torch.cuda.synchronize()
+    assert np.array_equal(Wp.cpu().view(torch.int16).numpy(), _pack_numpy(W.cpu().view(torch.int16).numpy()))
+    No = N // 2 if sw else N
+    Y0 = torch.full((B, No), float("nan"), device=DEV, dtype=torch.float16)
+    Y1 = torch.full((B, No), float("nan"), device=DEV, dtype=torch.float16)
+    _lib.check(lib.vcb_op_skinny_gemm_f16(_lib.ptr(X), K, _lib.ptr(W), B, N, K, _lib.ptr(R), N, sw, _lib.ptr(Y0), No, ST))
+    _lib.check(lib.vcb_op_skinny_gemm_packed_f16(_lib.ptr(X), K, _lib.ptr(Wp), B, N, K, _lib.ptr(R), N, sw, _lib.ptr(Y1), No, ST))
+    torch.cuda.synchronize()
+    assert not torch.isnan(Y1.float()).any()
+    assert torch.equal(Y0.view(torch.int16), Y1.view(torch.int16)), max_abs(Y0, Y1)
+
+
+def test_engine_with_packed_weight_stream_matches_row_major(monkeypatch):
+    """VCB_SKINNY_PACKED=1: the handle keeps a tile-major copy of every matrix the decode step streams; ids and logits must
+    equal the row-major engine's bit for bit (and therefore the oracle's / the reference fixtures' as tested above)."""
+    g = synth.PRESETS["tiny"].with_variant(synth.VARIANT_VCODER_DS)
+    sd = synth.make_state_dict(g, seed=0)
+    ids = synth.make_prompt_ids(g, 2, seed=4, n_before=6, n_after=5)
+    px = [synth.make_pixels(g, 2, s) for s in (1, 2, 3)]
+    outs = []
+    for packed in ("0", "1"):
+        monkeypatch.setenv("VCB_SKINNY_PACKED", packed)
+        eng = Engine(g, max_batch=2, max_seq_len=128)
+        eng.bind(sd)
+        pre = eng.prefill(ids, *px, want_logits=True)
+        dec, lg = eng.decode(5, want_logits=True)
+        gen = eng.generate(ids, *px, max_new_tokens=8)  # CUDA-graph path
+        torch.cuda.synchronize()
+        outs.append((pre["logits"].clone(), dec.clone(), lg.clone(), gen.clone()))
+        eng.close()
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)

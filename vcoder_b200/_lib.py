@@ -54,6 +54,8 @@ SIGNATURES = {
     "vcb_device_count": (C.c_int, []),
     "vcb_op_gemm_f16": (C.c_int, [_p, _i32, _p, _i32, _i32, _i32, _i32, _p, _p, _i32, _i32, _p, _i32, _i32, _p]),
     "vcb_op_skinny_gemm_f16": (C.c_int, [_p, _i32, _p, _i32, _i32, _i32, _p, _i32, _i32, _p, _i32, _p]),
+    "vcb_op_pack_skinny_weights": (C.c_int, [_p, _i32, _i32, _p, _p]),
+    "vcb_op_skinny_gemm_packed_f16": (C.c_int, [_p, _i32, _p, _i32, _i32, _i32, _p, _i32, _i32, _p, _i32, _p]),
     "vcb_op_skinny_rmsnorm_gemm_f16": (C.c_int, [_p, _i32, _p, _f, _p, _i32, _i32, _i32, _p, _i32, _i32, _p, _i32, _p]),
     "vcb_op_layernorm_f16": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _f, _p]),
     "vcb_op_rmsnorm_f16": (C.c_int, [_p, _p, _p, _i64, _i32, _f, _p]),

@@ -80,6 +80,22 @@ int vcb_op_skinny_gemm_f16(const vcb_half* X, int32_t ldx, const vcb_half* W, in
   return skinny_gemm(s, ST(stream));
 }
 
+int vcb_op_pack_skinny_weights(const vcb_half* W, int32_t N, int32_t K, vcb_half* Wp, void* stream) {
+  VCB_TRY(require_device());
+  return pack_skinny_weights(H(W), H(Wp), N, K, ST(stream));
+}
+
+int vcb_op_skinny_gemm_packed_f16(const vcb_half* X, int32_t ldx, const vcb_half* Wp, int32_t B, int32_t N, int32_t K,
+                                  const vcb_half* residual, int32_t ldr, int32_t swiglu, vcb_half* Y, int32_t ldy,
+                                  void* stream) {
+  VCB_TRY(require_device());
+  VCB_CHECK(Wp != nullptr, kErrInvalid, "vcb_op_skinny_gemm_packed_f16: Wp is null");
+  SkinnyParams s;
+  s.X = H(X); s.ldx = ldx; s.W = H(Wp); s.Wp = H(Wp); s.Y = H(Y); s.ldy = ldy; s.residual = H(residual); s.ldr = ldr;
+  s.B = B; s.N = N; s.K = K; s.swiglu = swiglu;
+  return skinny_gemm_tma(s, ST(stream));
+}
+
 int vcb_op_skinny_rmsnorm_gemm_f16(const vcb_half* X, int32_t ldx, const vcb_half* norm_w, float eps, const vcb_half* W,
                                    int32_t B, int32_t N, int32_t K, const vcb_half* residual, int32_t ldr, int32_t swiglu,
                                    vcb_half* Y, int32_t ldy, void* stream) {

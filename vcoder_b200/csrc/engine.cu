@@ -15,6 +15,8 @@ namespace vcb {
 
 namespace {
 
+constexpr bool kPackedDefault = false;  // VCB_SKINNY_PACKED unset: decode streams the row-major weights through the tensor map
+
 int dev_alloc(Engine* e, DevBuf* b, size_t bytes) {
   bytes = (bytes + 255) & ~static_cast<size_t>(255);
   void* p = nullptr;
@@ -143,10 +145,18 @@ int engine_create(const vcb_config* c, int device, Engine** out) {
   ALLOC(e->final_norm, H);
   ALLOC(e->lm_head, V * H);
   e->llm.resize(c->llm_layers);
+  {
+    // second, tile-major copy of every matrix the decode step streams: costs the LLM weight bytes again
+    // (13.2 GB at 7B, 25.7 GB at 13B of 180 GB) and turns the stream into linear 8 KiB bulk copies
+    const char* ev = getenv("VCB_SKINNY_PACKED");
+    e->use_packed = ev ? atoi(ev) != 0 : kPackedDefault;
+  }
   for (auto& l : e->llm) {
     ALLOC(l.qkv_w, 3 * H * H); ALLOC(l.o_w, H * H); ALLOC(l.gu_w, 2 * FF * H); ALLOC(l.down_w, H * FF);
     ALLOC(l.ln1, H); ALLOC(l.ln2, H);
+    if (e->use_packed) { ALLOC(l.qkv_p, 3 * H * H); ALLOC(l.o_p, H * H); ALLOC(l.gu_p, 2 * FF * H); ALLOC(l.down_p, H * FF); }
   }
+  if (e->use_packed) { ALLOC(e->lm_head_p, V * H); }
   // vision workspaces
   ALLOC(e->pix, NI * 3 * c->vit_image_size * c->vit_image_size);
   ALLOC(e->im2col, NI * e->P * e->Kpe);
@@ -302,8 +312,26 @@ int engine_bind(Engine* e, const vcb_tensor* ts, int n) {
       used = false;
     }
     VCB_TRY(rc);
-    if (used) e->bound.insert(name);
+    if (used) {
+      e->bound.insert(name);
+      e->packed_valid = false;
+    }
   }
+  return kOk;
+}
+
+int engine_ensure_packed(Engine* e, cudaStream_t st) {
+  if (!e->use_packed || e->packed_valid) return kOk;
+  const vcb_config& c = e->cfg;
+  const int H = c.llm_hidden, FF = c.llm_ffn, V = c.llm_vocab;
+  for (auto& l : e->llm) {
+    VCB_TRY(pack_skinny_weights(l.qkv_w.as<__half>(), l.qkv_p.as<__half>(), 3 * H, H, st));
+    VCB_TRY(pack_skinny_weights(l.o_w.as<__half>(), l.o_p.as<__half>(), H, H, st));
+    VCB_TRY(pack_skinny_weights(l.gu_w.as<__half>(), l.gu_p.as<__half>(), 2 * FF, H, st));
+    VCB_TRY(pack_skinny_weights(l.down_w.as<__half>(), l.down_p.as<__half>(), H, FF, st));
+  }
+  VCB_TRY(pack_skinny_weights(e->lm_head.as<__half>(), e->lm_head_p.as<__half>(), V, H, st));
+  e->packed_valid = true;
   return kOk;
 }
 
@@ -608,6 +636,7 @@ int engine_prefill(Engine* e, const int64_t* ids, int B, int T, const void* imag
   const bool ds = c.variant == VCB_VARIANT_VCODER_DS;
   const bool multimodal = images != nullptr;  // reference: `images is None` -> plain LLaMA path (arch.py:130)
   VCB_TRY(engine_check_bound(e, multimodal, true));
+  VCB_TRY(engine_ensure_packed(e, st));
   VCB_CHECK(ds || depths == nullptr, kErrInvalid, "only VCoder-DS takes depth images");
   VCB_CHECK(c.variant != VCB_VARIANT_LLAVA || segs == nullptr, kErrInvalid, "LLaVA takes no seg images");
   const int H = c.llm_hidden, FF = c.llm_ffn, V = c.llm_vocab, S = e->S;
@@ -770,7 +799,7 @@ int engine_prefill(Engine* e, const int64_t* ids, int B, int T, const void* imag
   {
     SkinnyParams s;  // final RMSNorm fused into the lm_head GEMM
     s.norm_w = e->final_norm.as<__half>(); s.norm_eps = c.llm_rms_eps;
-    s.X = xd; s.ldx = H; s.W = e->lm_head.as<__half>(); s.Y = e->logits.as<__half>(); s.ldy = V;
+    s.X = xd; s.ldx = H; s.W = e->lm_head.as<__half>(); s.Wp = e->lm_head_p.as<__half>(); s.Y = e->logits.as<__half>(); s.ldy = V;
     s.B = B; s.N = V; s.K = H;
     VCB_TRY(skinny_gemm(s, st));
   }
@@ -820,7 +849,7 @@ int decode_step_launch(Engine* e, int max_ctx, cudaStream_t st) {
     {
       SkinnyParams s;
       if (fuse_norm) { s.norm_w = l.ln1.as<__half>(); s.norm_eps = c.llm_rms_eps; }
-      s.X = fuse_norm ? x : xn; s.ldx = H; s.W = l.qkv_w.as<__half>(); s.Y = qkv; s.ldy = 3 * H; s.B = B; s.N = 3 * H; s.K = H;
+      s.X = fuse_norm ? x : xn; s.ldx = H; s.W = l.qkv_w.as<__half>(); s.Wp = l.qkv_p.as<__half>(); s.Y = qkv; s.ldy = 3 * H; s.B = B; s.N = 3 * H; s.K = H;
       VCB_TRY(skinny_gemm(s, st));
     }
     if (!fuse_rope)
@@ -839,7 +868,7 @@ int decode_step_launch(Engine* e, int max_ctx, cudaStream_t st) {
     }
     {
       SkinnyParams s;
-      s.X = e->attnd.as<__half>(); s.ldx = H; s.W = l.o_w.as<__half>(); s.Y = x; s.ldy = H; s.residual = x; s.ldr = H;
+      s.X = e->attnd.as<__half>(); s.ldx = H; s.W = l.o_w.as<__half>(); s.Wp = l.o_p.as<__half>(); s.Y = x; s.ldy = H; s.residual = x; s.ldr = H;
       s.B = B; s.N = H; s.K = H;
       VCB_TRY(skinny_gemm(s, st));
     }
@@ -847,13 +876,13 @@ int decode_step_launch(Engine* e, int max_ctx, cudaStream_t st) {
     {
       SkinnyParams s;
       if (fuse_norm) { s.norm_w = l.ln2.as<__half>(); s.norm_eps = c.llm_rms_eps; }
-      s.X = fuse_norm ? x : xn; s.ldx = H; s.W = l.gu_w.as<__half>(); s.Y = e->midd.as<__half>(); s.ldy = FF; s.B = B; s.N = 2 * FF;
+      s.X = fuse_norm ? x : xn; s.ldx = H; s.W = l.gu_w.as<__half>(); s.Wp = l.gu_p.as<__half>(); s.Y = e->midd.as<__half>(); s.ldy = FF; s.B = B; s.N = 2 * FF;
       s.K = H; s.swiglu = 1;
       VCB_TRY(skinny_gemm(s, st));
     }
     {
       SkinnyParams s;
-      s.X = e->midd.as<__half>(); s.ldx = FF; s.W = l.down_w.as<__half>(); s.Y = x; s.ldy = H; s.residual = x; s.ldr = H;
+      s.X = e->midd.as<__half>(); s.ldx = FF; s.W = l.down_w.as<__half>(); s.Wp = l.down_p.as<__half>(); s.Y = x; s.ldy = H; s.residual = x; s.ldr = H;
       s.B = B; s.N = H; s.K = FF;
       VCB_TRY(skinny_gemm(s, st));
     }
@@ -862,7 +891,7 @@ int decode_step_launch(Engine* e, int max_ctx, cudaStream_t st) {
   {
     SkinnyParams s;
     if (fuse_norm) { s.norm_w = e->final_norm.as<__half>(); s.norm_eps = c.llm_rms_eps; }
-    s.X = fuse_norm ? x : xn; s.ldx = H; s.W = e->lm_head.as<__half>(); s.Y = e->logits.as<__half>(); s.ldy = V; s.B = B; s.N = V; s.K = H;
+    s.X = fuse_norm ? x : xn; s.ldx = H; s.W = e->lm_head.as<__half>(); s.Wp = e->lm_head_p.as<__half>(); s.Y = e->logits.as<__half>(); s.ldy = V; s.B = B; s.N = V; s.K = H;
     VCB_TRY(skinny_gemm(s, st));
   }
   VCB_TRY(select_next(e, B, counters + 1, st));
@@ -1054,10 +1083,11 @@ int engine_bench_weight_stream(Engine* e, int B, int rounds, float* ms_total, in
   VCB_CUDA(cudaEventCreate(&a));
   VCB_CUDA(cudaEventCreate(&b));
   int n = 0, rc = kOk;
-  auto run = [&](const __half* X, long ldx, const DevBuf& W, __half* Y, long ldy, int N, int K, int swiglu) {
+  VCB_TRY(engine_ensure_packed(e, st));
+  auto run = [&](const __half* X, long ldx, const DevBuf& W, const DevBuf& Wp, __half* Y, long ldy, int N, int K, int swiglu) {
     if (rc != kOk) return;
     SkinnyParams s;
-    s.X = X; s.ldx = ldx; s.W = W.as<__half>(); s.Y = Y; s.ldy = ldy; s.B = B; s.N = N; s.K = K; s.swiglu = swiglu;
+    s.X = X; s.ldx = ldx; s.W = W.as<__half>(); s.Wp = Wp.as<__half>(); s.Y = Y; s.ldy = ldy; s.B = B; s.N = N; s.K = K; s.swiglu = swiglu;
     rc = skinny_gemm(s, st);
     ++n;
   };
@@ -1065,12 +1095,12 @@ int engine_bench_weight_stream(Engine* e, int B, int rounds, float* ms_total, in
     if (r == 0) { n = 0; cudaEventRecord(a, st); }
     for (int li = 0; li < c.llm_layers; ++li) {
       const LlmLayerW& l = e->llm[li];
-      run(e->xnd.as<__half>(), H, l.qkv_w, e->qkvd.as<__half>(), 3 * H, 3 * H, H, 0);
-      run(e->attnd.as<__half>(), H, l.o_w, e->xd.as<__half>(), H, H, H, 0);
-      run(e->xnd.as<__half>(), H, l.gu_w, e->midd.as<__half>(), FF, 2 * FF, H, 1);
-      run(e->midd.as<__half>(), FF, l.down_w, e->xd.as<__half>(), H, H, FF, 0);
+      run(e->xnd.as<__half>(), H, l.qkv_w, l.qkv_p, e->qkvd.as<__half>(), 3 * H, 3 * H, H, 0);
+      run(e->attnd.as<__half>(), H, l.o_w, l.o_p, e->xd.as<__half>(), H, H, H, 0);
+      run(e->xnd.as<__half>(), H, l.gu_w, l.gu_p, e->midd.as<__half>(), FF, 2 * FF, H, 1);
+      run(e->midd.as<__half>(), FF, l.down_w, l.down_p, e->xd.as<__half>(), H, H, FF, 0);
     }
-    run(e->xnd.as<__half>(), H, e->lm_head, e->logits.as<__half>(), V, V, H, 0);
+    run(e->xnd.as<__half>(), H, e->lm_head, e->lm_head_p, e->logits.as<__half>(), V, V, H, 0);
   }
   cudaEventRecord(b, st);
   cudaError_t se = cudaStreamSynchronize(st);

@@ -33,6 +33,7 @@ struct ProjW {
 };
 struct LlmLayerW {
   DevBuf qkv_w, o_w, gu_w, down_w, ln1, ln2;
+  DevBuf qkv_p, o_p, gu_p, down_p;  // tile-major copies for the decode weight stream (pack_skinny_weights), if enabled
 };
 
 struct Engine {
@@ -51,7 +52,9 @@ struct Engine {
   DevBuf patch_w, cls, pos, preln_w, preln_b;
   std::vector<VitLayerW> vit;
   ProjW mm, seg;
-  DevBuf embed, final_norm, lm_head;
+  DevBuf embed, final_norm, lm_head, lm_head_p;
+  bool use_packed = false;    // decode GEMMs stream the tile-major weight copies (VCB_SKINNY_PACKED)
+  bool packed_valid = false;  // the copies reflect the bound weights
   std::vector<LlmLayerW> llm;
   std::set<std::string> bound;
 
@@ -97,6 +100,7 @@ struct Engine {
 int engine_create(const vcb_config* cfg, int device, Engine** out);
 int engine_bind(Engine* e, const vcb_tensor* t, int n);
 int engine_check_bound(Engine* e, bool need_vision, bool need_llm);
+int engine_ensure_packed(Engine* e, cudaStream_t st);
 // images: device pointer to n images [n,3,S,S] fp16 already resident; result rows in e->vh ([n*S, D])
 int engine_tower(Engine* e, const __half* pixels_dev, int n_images, cudaStream_t st);
 int engine_project(Engine* e, int row_begin, int row_end, const ProjW& w, cudaStream_t st);

@@ -60,6 +60,8 @@ struct SkinnyParams {
   const __half* X = nullptr;  // [B, K], ldx
   long ldx = 0;
   const __half* W = nullptr;  // [N, K] row-major
+  const __half* Wp = nullptr; // optional tile-major copy of W made by pack_skinny_weights: the weight stream then reads
+                              // this instead of W (linear 8 KiB bulk copies instead of 16 x 512-byte tensor-map boxes)
   __half* Y = nullptr;        // [B, N_out], ldy
   long ldy = 0;
   const __half* residual = nullptr;  // [B, N], ldr (may alias Y)
@@ -74,6 +76,9 @@ struct SkinnyParams {
   float norm_eps = 0.f;
 };
 int skinny_gemm(const SkinnyParams& p, cudaStream_t stream);
+int skinny_gemm_tma(const SkinnyParams& p, cudaStream_t stream);  // TMA / bulk-copy fed kernel (skinny_tma.cu); needs K % 64 == 0
+// W[N,K] row-major -> the streaming layout of the decode GEMM: [N/16][K/64][16 rows][128 B, 16-byte chunks pre-swizzled]
+int pack_skinny_weights(const __half* W, __half* Wp, int N, int K, cudaStream_t stream);
 
 // ---- elementwise / normalisation / data movement ----------------------------------------------------------
 int im2col_patches(const __half* pixels, __half* out, int B, int image, int patch, int k_pad, cudaStream_t s);

@@ -6,6 +6,7 @@
 // kernel runs out of.  Programmatic dependent launch: ring fill happens BEFORE the grid-dependency wait — weights do
 // not depend on the previous kernel, so HBM keeps streaming across kernel boundaries.
 #include <cstdlib>
+#include <cstring>
 
 #include "common.h"
 #include "kernels.h"
@@ -34,8 +35,19 @@ __device__ __forceinline__ uint32_t hmul2_u32(uint32_t a, uint32_t b) {
 }
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + fast_exp2(-1.4426950408889634f * x)); }
 
-// W viewed as a 3-D tensor [K/64][N][64]: dim0 = k within a 64-block, dim1 = row, dim2 = k-block
-template <int NB, int WARPS, int kDepth, int kGroup>
+// 1-D bulk copy global -> shared, completion on an mbarrier (no tensor map: the source is already the smem image)
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// W viewed as a 3-D tensor [K/64][N][64]: dim0 = k within a 64-block, dim1 = row, dim2 = k-block.
+// PACKED: the weight stream comes from the tile-major copy made by pack_skinny_weights (p.Wp): the 16 x K slab of a CTA is
+// one contiguous 32*K-byte run of 2 KiB blocks [k-block][16 rows][128 B, chunks pre-swizzled], so a stage is ONE linear
+// 8 KiB bulk copy and every DRAM page the stream touches is consumed completely (the row-major source gives 512-byte runs
+// at an 8 KiB stride).
+template <int NB, int WARPS, int kDepth, int kGroup, bool PACKED>
 __global__ void __launch_bounds__(WARPS * 32)
 skinny_tma_kernel(const __grid_constant__ CUtensorMap tmW, SkinnyParams p) {
   constexpr int kStageBytes = kGroup * 16 * kKBlk * 2;  // kGroup k-blocks x 16 rows x 128 B
@@ -53,20 +65,31 @@ skinny_tma_kernel(const __grid_constant__ CUtensorMap tmW, SkinnyParams p) {
   if ((smem_u32(smem) & 1023u) != 0) __trap();
 
   // this warp's range of k-groups (a group = 4 k-blocks = 256 k)
-  const int n_groups = (p.K / kKBlk + kGroup - 1) / kGroup;
+  const int n_kblocks = p.K / kKBlk;
+  const int n_groups = (n_kblocks + kGroup - 1) / kGroup;
   const int per = (n_groups + WARPS - 1) / WARPS;
   const int g_begin = min(n_groups, warp * per), g_end = min(n_groups, g_begin + per);
   const int my_groups = g_end - g_begin;
 
+  // one stage = k-group `grp` of this CTA's 16 rows
+  auto issue = [&](int s, int grp) {
+    const uint32_t b = smem_u32(&bars[warp][s]);
+    if constexpr (PACKED) {
+      const int kb0 = grp * kGroup;
+      const uint32_t bytes = static_cast<uint32_t>(min(kGroup, n_kblocks - kb0)) * 2048u;  // last group may be short
+      mbar_expect_tx(b, bytes);
+      bulk_load_1d(ring + s * kStageBytes,
+                   reinterpret_cast<const uint8_t*>(p.Wp) + (static_cast<size_t>(blockIdx.x) * n_kblocks + kb0) * 2048u, bytes, b);
+    } else {
+      mbar_expect_tx(b, kStageBytes);
+      tma_load_3d(ring + s * kStageBytes, &tmW, b, 0, row0, grp * kGroup);
+    }
+  };
   if (lane == 0) {
     for (int s = 0; s < kDepth; ++s) mbar_init(smem_u32(&bars[warp][s]), 1);
     fence_mbar_init();
-    tma_prefetch_desc(&tmW);
-    for (int s = 0; s < kDepth && s < my_groups; ++s) {  // fill the ring before waiting on the previous kernel
-      const uint32_t b = smem_u32(&bars[warp][s]);
-      mbar_expect_tx(b, kStageBytes);
-      tma_load_3d(ring + s * kStageBytes, &tmW, b, 0, row0, (g_begin + s) * kGroup);
-    }
+    if constexpr (!PACKED) tma_prefetch_desc(&tmW);
+    for (int s = 0; s < kDepth && s < my_groups; ++s) issue(s, g_begin + s);  // fill the ring before waiting on the previous kernel
   }
   __syncwarp();
   griddep_wait();  // X (and the residual) come from the previous kernel
@@ -128,6 +151,8 @@ skinny_tma_kernel(const __grid_constant__ CUtensorMap tmW, SkinnyParams p) {
     const uint32_t st = ring + s * kStageBytes;
 #pragma unroll
     for (int kb = 0; kb < kGroup; ++kb) {
+      // a short last group leaves stale bytes behind the copied k-blocks (the tensor-map path zero-fills them instead)
+      if (PACKED && (g_begin + i) * kGroup + kb >= n_kblocks) continue;
 #pragma unroll
       for (int hlf = 0; hlf < 2; ++hlf) {
         // 32-k chunk (kb, hlf): thread t takes 16-byte chunk 4*hlf + t of rows g and g+8 (swizzle: chunk ^ (row & 7))
@@ -146,11 +171,7 @@ skinny_tma_kernel(const __grid_constant__ CUtensorMap tmW, SkinnyParams p) {
       }
     }
     __syncwarp();  // every lane is done with stage s before it is refilled
-    if (lane == 0 && i + kDepth < my_groups) {
-      const uint32_t b = smem_u32(&bars[warp][s]);
-      mbar_expect_tx(b, kStageBytes);
-      tma_load_3d(st, &tmW, b, 0, row0, (g_begin + i + kDepth) * kGroup);
-    }
+    if (lane == 0 && i + kDepth < my_groups) issue(s, g_begin + i + kDepth);
     if (i + 1 < my_groups) {
 #pragma unroll
       for (int c = 0; c < 2 * kGroup; ++c)
@@ -219,18 +240,39 @@ skinny_tma_kernel(const __grid_constant__ CUtensorMap tmW, SkinnyParams p) {
   }
 }
 
-template <int NB, int WARPS, int kDepth, int kGroup>
+template <int NB, int WARPS, int kDepth, int kGroup, bool PACKED = false>
 int launch_tma(const CUtensorMap& tm, const SkinnyParams& p, int grid, cudaStream_t stream) {
   constexpr int kStageBytes = kGroup * 16 * kKBlk * 2;
   constexpr int smem = WARPS * kDepth * kStageBytes + WARPS * 16 * (8 * NB + 1) * 4 + 8 + WARPS * kDepth * 8 + WARPS * 8 * NB * 4 + 16;
   static_assert(smem <= 227 * 1024, "skinny_tma: ring does not fit in shared memory");
   static bool attr = false;
   if (!attr) {
-    VCB_CUDA(cudaFuncSetAttribute(skinny_tma_kernel<NB, WARPS, kDepth, kGroup>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    VCB_CUDA(cudaFuncSetAttribute(skinny_tma_kernel<NB, WARPS, kDepth, kGroup, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr = true;
   }
-  VCB_CUDA(launch_pdl(skinny_tma_kernel<NB, WARPS, kDepth, kGroup>, dim3(grid), dim3(WARPS * 32), smem, stream, tm, p));
+  VCB_CUDA(launch_pdl(skinny_tma_kernel<NB, WARPS, kDepth, kGroup, PACKED>, dim3(grid), dim3(WARPS * 32), smem, stream, tm, p));
   return kOk;
+}
+// packed weight stream: the measured-best ring shape (4 warps x 2 stages x 8 KiB), or 3 stages (VCB_SKINNY_TMA_DEPTH=3)
+template <int NB>
+int launch_packed(const SkinnyParams& p, int grid, int depth, cudaStream_t stream) {
+  CUtensorMap unused;
+  memset(&unused, 0, sizeof(unused));
+  if (depth >= 3) return launch_tma<NB, 4, 3, 4, true>(unused, p, grid, stream);
+  return launch_tma<NB, 4, 2, 4, true>(unused, p, grid, stream);
+}
+
+// row-major W[N,K] -> tile-major, pre-swizzled copy (one thread per 16-byte chunk): chunk c of row n goes to
+// ((tile * K/64 + kb) * 16 + r) * 8 + (ch ^ (r & 7)) with tile = n/16, r = n%16, kb = c/8, ch = c%8 — exactly the shared
+// memory image the 128B-swizzled tensor-map load of the same k-block produces
+__global__ void pack_skinny_kernel(const uint4* __restrict__ W, uint4* __restrict__ Wp, int N, int K) {
+  const long cpr = K / 8;  // chunks per row
+  const long total = static_cast<long>(N) * cpr;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long n = i / cpr, c = i % cpr;
+    const long tile = n >> 4, r = n & 15, kb = c >> 3, ch = c & 7;
+    Wp[((tile * (K / 64) + kb) * 16 + r) * 8 + (ch ^ (r & 7))] = W[i];
+  }
 }
 template <int NB>
 int launch_tma_w(const CUtensorMap& tm, const SkinnyParams& p, int grid, int warps, int depth, int group,
@@ -253,11 +295,34 @@ int launch_tma_w(const CUtensorMap& tm, const SkinnyParams& p, int grid, int war
 
 int make_tmap_w3d(CUtensorMap* m, const void* ptr, uint64_t K, uint64_t N, uint32_t box_kblocks);
 
+int pack_skinny_weights(const __half* W, __half* Wp, int N, int K, cudaStream_t stream) {
+  VCB_CHECK(W != nullptr && Wp != nullptr && N % 16 == 0 && K % 64 == 0, kErrInvalid,
+            "pack_skinny_weights: N % 16 and K % 64 must be 0");
+  VCB_CHECK((reinterpret_cast<uintptr_t>(W) & 15) == 0 && (reinterpret_cast<uintptr_t>(Wp) & 15) == 0, kErrInvalid,
+            "pack_skinny_weights: pointers must be 16-byte aligned");
+  KernelScope scope(kCatMisc, stream);
+  pack_skinny_kernel<<<8 * device_sm_count(), 256, 0, stream>>>(reinterpret_cast<const uint4*>(W), reinterpret_cast<uint4*>(Wp), N, K);
+  VCB_CUDA(cudaGetLastError());
+  return kOk;
+}
+
 int skinny_gemm_tma(const SkinnyParams& p, cudaStream_t stream) {
   VCB_CHECK(p.B >= 1 && p.B <= 32, kErrInvalid, "skinny_gemm: batch must be in [1, 32]");
   VCB_CHECK(p.N % 16 == 0 && p.K % 64 == 0, kErrInvalid, "skinny_gemm_tma: N % 16 and K % 64 must be 0");
   const int grid = p.N / 16;
   const int nb = (p.B + 7) / 8;
+  if (p.Wp != nullptr) {
+    VCB_CHECK((reinterpret_cast<uintptr_t>(p.Wp) & 15) == 0, kErrInvalid, "skinny_gemm: packed weights must be 16-byte aligned");
+    static int env_pd = -1;
+    if (env_pd < 0) { const char* e = getenv("VCB_SKINNY_TMA_DEPTH"); env_pd = e ? atoi(e) : 0; }
+    KernelScope scope(kCatSkinny, stream);
+    switch (nb) {
+      case 1: return launch_packed<1>(p, grid, env_pd, stream);
+      case 2: return launch_packed<2>(p, grid, env_pd, stream);
+      case 3: return launch_packed<3>(p, grid, env_pd, stream);
+      default: return launch_packed<4>(p, grid, env_pd, stream);
+    }
+  }
   int warps = 4;  // 4 warps x 3 stages x 8 KiB = 96 KiB per CTA -> two CTAs per SM
   int depth = 2, group = 4;  // measured best on B200: 4 warps x 2 stages x 8 KiB -> three CTAs per SM
   static int env_w = -1, env_d = -1, env_g = -1;
