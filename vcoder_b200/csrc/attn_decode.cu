@@ -37,11 +37,25 @@ attn_decode_split_kernel(AttnDecodeParams p, int splits) {
   __shared__ float s_acc[8][kDH];
   __shared__ float s_m[8], s_l[8];
   griddep_launch();
-  griddep_wait();  // q and the current token's K/V row come from the kernels just before this one
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x, hw = tid >> 4, l16 = tid & 15;
-  const int ctx = *p.ctx_len;
   const int k0 = split * kChunk;
+  if (p.prefetch && tid == 0) {
+    // While the QKV GEMM drains: pull this split's K/V pages (16 KiB contiguous per page and head, written in earlier
+    // steps) into L2.  The context length read here may still be the previous step's — a lower bound is all this needs.
+    const int ctx0 = *reinterpret_cast<const volatile int32_t*>(p.ctx_len);
+    if (k0 < ctx0) {
+      const int nt = (min(kChunk, ctx0 - k0) + kPT - 1) / kPT;
+      const int32_t* bt0 = p.block_table + b * p.max_pages + k0 / kPT;
+      for (int t = 0; t < nt; ++t) {
+        const long off = (static_cast<long>(bt0[t]) * p.n_heads + h) * kPT * kDH;
+        bulk_prefetch_l2(p.k_pool + off, kPT * kDH * 2);
+        bulk_prefetch_l2(p.v_pool + off, kPT * kDH * 2);
+      }
+    }
+  }
+  griddep_wait();  // q and the current token's K/V row come from the kernels just before this one
+  const int ctx = *p.ctx_len;
   const long pidx = (static_cast<long>(b) * p.n_heads + h) * splits + split;
   if (k0 >= ctx) {
     if (tid == 0) { p.part_ml[pidx * 2] = -INFINITY; p.part_ml[pidx * 2 + 1] = 0.f; }
@@ -201,7 +215,11 @@ attn_decode_combine_kernel(AttnDecodeParams p, int splits) {
 
 int attn_decode_splits(int max_ctx) { return (max_ctx + kChunk - 1) / kChunk; }
 
-int attn_llama_decode(const AttnDecodeParams& p, cudaStream_t stream) {
+int attn_llama_decode(const AttnDecodeParams& p_in, cudaStream_t stream) {
+  AttnDecodeParams p = p_in;
+  static int env_pf = -1;  // VCB_ATTN_DEC_PF=1: L2-prefetch the split's KV pages before the grid-dependency wait
+  if (env_pf < 0) { const char* e = getenv("VCB_ATTN_DEC_PF"); env_pf = e ? atoi(e) : 0; }
+  p.prefetch = env_pf;
   const int splits = attn_decode_splits(p.max_ctx);
   VCB_CHECK(splits >= 1, kErrInvalid, "attn_llama_decode: empty context");
   VCB_CHECK(p.page_tokens == kPT, kErrInvalid, "attn_llama_decode: KV page must hold 64 tokens");

@@ -50,6 +50,7 @@ struct AttnDecodeParams {
   float* part_ml = nullptr;          // [B*heads, splits, 2]
   __half* out = nullptr;             // [B, H]
   int batch = 0, n_heads = 0;
+  int prefetch = 0;  // L2-prefetch the split's KV pages before the grid-dependency wait (VCB_ATTN_DEC_PF)
   float scale = 1.f;
 };
 int attn_llama_decode(const AttnDecodeParams& p, cudaStream_t stream);
@@ -70,6 +71,8 @@ struct SkinnyParams {
   int swiglu = 0;  // W rows 8/8 interleaved gate|up; N_out = N/2
   int mode = 1;    // chunk->warp mapping (see skinny.cu)
   int prefetch = 0;  // cp.async.bulk.prefetch.L2 ahead of the demand loads (measured slower: off)
+  int pf_groups = 0;  // TMA kernel: k-groups per warp prefetched into L2 before the grid-dependency wait (first wave only)
+  int pf_ctas = 0;    // CTAs that count as the first wave
   int double_buffer = 0;  // keep the next batch of weight loads in flight during the MMAs (costs registers)
   // fused LlamaRMSNorm on X (decode): Y = rsqrt(mean(x^2)+eps) * W (x o norm_w); null = X is used as is
   const __half* norm_w = nullptr;

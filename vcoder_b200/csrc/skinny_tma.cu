@@ -16,6 +16,7 @@ namespace vcb {
 namespace {
 
 constexpr int kKBlk = 64;               // k elements per 128-byte swizzled row
+constexpr int kPrefetchGroupsDefault = 0;  // see DESIGN.md section 3.1 for the measurement behind this default
 
 __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                           uint32_t b0, uint32_t b1) {
@@ -39,6 +40,14 @@ __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + f
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// L2 prefetches (no shared-memory destination, no completion tracking): issued BEFORE the grid-dependency wait for the
+// k-groups right behind the ring, so HBM keeps working through the kernel boundary and the first ring refills hit L2
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* m, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
 
@@ -90,6 +99,20 @@ skinny_tma_kernel(const __grid_constant__ CUtensorMap tmW, SkinnyParams p) {
     fence_mbar_init();
     if constexpr (!PACKED) tma_prefetch_desc(&tmW);
     for (int s = 0; s < kDepth && s < my_groups; ++s) issue(s, g_begin + s);  // fill the ring before waiting on the previous kernel
+    // CTAs of the first wave sit at the grid-dependency wait while the previous kernel drains: pull the next k-groups of
+    // their slab into L2 meanwhile (later waves start after the wait has long been released and would only add requests)
+    if (p.pf_groups > 0 && static_cast<int>(blockIdx.x) < p.pf_ctas) {
+      const int g0 = g_begin + kDepth, g1 = min(g_end, g0 + p.pf_groups);
+      if constexpr (PACKED) {
+        if (g1 > g0) {
+          const int kb0 = g0 * kGroup, kb1 = min(n_kblocks, g1 * kGroup);
+          bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.Wp) + (static_cast<size_t>(blockIdx.x) * n_kblocks + kb0) * 2048u,
+                           static_cast<uint32_t>(kb1 - kb0) * 2048u);
+        }
+      } else {
+        for (int grp = g0; grp < g1; ++grp) tma_prefetch_3d(&tmW, 0, row0, grp * kGroup);
+      }
+    }
   }
   __syncwarp();
   griddep_wait();  // X (and the residual) come from the previous kernel
@@ -306,11 +329,19 @@ int pack_skinny_weights(const __half* W, __half* Wp, int N, int K, cudaStream_t 
   return kOk;
 }
 
-int skinny_gemm_tma(const SkinnyParams& p, cudaStream_t stream) {
+int skinny_gemm_tma(const SkinnyParams& p_in, cudaStream_t stream) {
+  SkinnyParams p = p_in;
   VCB_CHECK(p.B >= 1 && p.B <= 32, kErrInvalid, "skinny_gemm: batch must be in [1, 32]");
   VCB_CHECK(p.N % 16 == 0 && p.K % 64 == 0, kErrInvalid, "skinny_gemm_tma: N % 16 and K % 64 must be 0");
   const int grid = p.N / 16;
   const int nb = (p.B + 7) / 8;
+  {
+    static int env_pf = -1, env_pc = -1;  // VCB_SKINNY_PF: k-groups per warp prefetched into L2 before the dependency wait
+    if (env_pf < 0) { const char* e = getenv("VCB_SKINNY_PF"); env_pf = e ? atoi(e) : kPrefetchGroupsDefault; }
+    if (env_pc < 0) { const char* e = getenv("VCB_SKINNY_PF_CTAS"); env_pc = e ? atoi(e) : 3 * device_sm_count(); }
+    p.pf_groups = env_pf;
+    p.pf_ctas = env_pc;
+  }
   if (p.Wp != nullptr) {
     VCB_CHECK((reinterpret_cast<uintptr_t>(p.Wp) & 15) == 0, kErrInvalid, "skinny_gemm: packed weights must be 16-byte aligned");
     static int env_pd = -1;
