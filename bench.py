@@ -199,10 +199,13 @@ METRIC = "end-to-end tokens/sec (prefill+decode) VCoder-DS-7B bs8"
 
 
 def workload_config(args, world):
+    which = ("BASELINE.json configs[2]" if (args.preset, args.batch, args.new_tokens) == ("7b", 8, 128)
+             else "BASELINE.json configs[3], one GPU's slice of the batch-32 job" if (args.preset, args.batch, args.new_tokens) == ("13b", 4, 256)
+             else "non-headline shape")
     return {"workload": f"VCoder-DS LLaVA-1.5-{args.preset.upper()}, RGB+seg+depth towers (CLIP ViT-L/14@336), batch {args.batch} "
-                        f"per GPU, prompt 58 ids -> T'=1207 spliced tokens, {args.new_tokens} new tokens, greedy (BASELINE.json configs[2])",
+                        f"per GPU, prompt 58 ids -> T'=1207 spliced tokens, {args.new_tokens} new tokens, greedy ({which})",
             "global_batch": args.batch * world, "new_tokens": args.new_tokens, "parallelism": f"dp{world} (replicas, one NCCL all-gather of ids)",
-            "l2": "inputs larger than L2: 13.5 GB of weights + KV streamed per decode step vs 126 MB L2; no explicit flush",
+            "l2": f"inputs larger than L2: {'13.5' if args.preset == '7b' else '26'} GB of weights + KV streamed per decode step vs 126 MB L2; no explicit flush",
             "weights": "seeded random-init fp16 (HF std 0.02)"}
 
 
@@ -378,8 +381,10 @@ def run_b200(args):
         cpu = cpu_sample_tokens_per_s(B, N, repeats=20)  # ~15 s of CPU work on the GPU box
     if rank == 0:
         h2d = sum(p.numel() * 2 for p in host_px) + ids.numel() * 8
+        headline = (args.preset, args.batch) == ("7b", 8)
         line = {
-            "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC if headline else f"end-to-end tokens/sec (prefill+decode) VCoder-DS-{args.preset.upper()} bs{args.batch}",
+            "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16", "data": "synthetic", "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * N * 4,

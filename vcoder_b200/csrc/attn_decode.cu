@@ -217,8 +217,8 @@ int attn_decode_splits(int max_ctx) { return (max_ctx + kChunk - 1) / kChunk; }
 
 int attn_llama_decode(const AttnDecodeParams& p_in, cudaStream_t stream) {
   AttnDecodeParams p = p_in;
-  static int env_pf = -1;  // VCB_ATTN_DEC_PF=1: L2-prefetch the split's KV pages before the grid-dependency wait
-  if (env_pf < 0) { const char* e = getenv("VCB_ATTN_DEC_PF"); env_pf = e ? atoi(e) : 0; }
+  static int env_pf = -1;  // VCB_ATTN_DEC_PF=0 turns off: L2-prefetch the split's KV pages before the grid-dependency wait
+  if (env_pf < 0) { const char* e = getenv("VCB_ATTN_DEC_PF"); env_pf = e ? atoi(e) : 1; }  // measured: DESIGN.md section 3.1
   p.prefetch = env_pf;
   const int splits = attn_decode_splits(p.max_ctx);
   VCB_CHECK(splits >= 1, kErrInvalid, "attn_llama_decode: empty context");
