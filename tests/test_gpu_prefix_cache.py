@@ -139,6 +139,14 @@ def test_cache_is_invalidated_by_other_entry_points():
     eng.reset()
     pre = eng.prefill(ids, *px, want_logits=True, reuse=True)
     assert not pre["towers_skipped"] and pre["reused_len"] == 0
+    # re-binding weights invalidates both the cached features and the cached KV entries
+    eng.bind({k: v for k, v in synth.make_state_dict(g, seed=1).items() if k.startswith("model.layers.0.")})
+    pre = eng.prefill(ids, *px, want_logits=True, reuse=True)
+    assert not pre["towers_skipped"] and pre["reused_len"] == 0
+    eng.bind(sd)
+    pre = eng.prefill(ids, *px, want_logits=True, reuse=True)
+    assert not pre["towers_skipped"] and pre["reused_len"] == 0
+    assert max_abs(pre["logits"], ref["logits"]) <= 2e-3
     # plain vcb_prefill never reuses, but what it leaves behind can be reused by the next cached call (text only:
     # it does not fingerprint its pixels)
     eng.prefill(ids, *px)

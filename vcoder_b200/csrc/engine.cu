@@ -315,6 +315,9 @@ int engine_bind(Engine* e, const vcb_tensor* ts, int n) {
     if (used) {
       e->bound.insert(name);
       e->packed_valid = false;
+      // new weights: neither the projected features nor the KV entries a later vcb_prefill_cached could reuse are valid
+      e->feat_key = 0;
+      e->seq_plan_len = 0;
     }
   }
   return kOk;
