@@ -13,6 +13,7 @@
 //   warps 2..5      : epilogue      — tcgen05.ld TMEM -> registers, bias / activation / residual, fp16 stores
 // Three mbarrier pipelines: smem full/empty (TMA<->MMA), TMEM full/empty (MMA<->epilogue), static tile round-robin.
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.h"
@@ -24,6 +25,7 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 fp16 = 128 bytes = one swizzle-128B row
 constexpr int kGemmThreads = 192;
+constexpr int kGemmPairDefault = 0;  // VCB_GEMM_PAIR unset: 1-CTA kernel (see DESIGN.md section 3 for the measurement)
 
 template <int BN>
 struct GemmCfg {
@@ -44,6 +46,70 @@ __device__ __forceinline__ float act_silu(float x) { return __fdividef(x, 1.0f +
 __device__ __forceinline__ void add_half8(float* v, const uint4& h) {
   float2 a = unpack_half2(h.x), b = unpack_half2(h.y), c = unpack_half2(h.z), d = unpack_half2(h.w);
   v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y; v[4] += c.x; v[5] += c.y; v[6] += d.x; v[7] += d.y;
+}
+
+// Epilogue of one accumulator row: `tmem_acc` = TMEM address of this thread's lane at the first column of the accumulator
+// buffer, m = global output row, n_base = first global column of the tile.  tcgen05.ld -> bias / activation / residual ->
+// fp16 stores (a thread owns one row, 32 columns at a time).
+template <int BN, int ACT>
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmEpilogue& ep, uint32_t tmem_acc, int m, int M, int N, int n_base) {
+  const bool row_ok = m < M;
+  long out_row = m;
+  if (ep.out_group) out_row = m + static_cast<long>(m / ep.out_group) * ep.out_skip + ep.out_off;
+  const long res_row = ep.res_mod ? static_cast<long>(m % ep.res_mod) + ep.res_off : out_row;
+#pragma unroll 1
+  for (int c = 0; c < BN; c += 32) {
+    const int n0 = n_base + c;
+    if (n0 >= N) break;
+    uint32_t r[32];
+    tmem_ld_32x32(tmem_acc + c, r);
+    tmem_ld_wait();
+    if (row_ok) {
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (ep.bias) {
+        const uint4* bp = reinterpret_cast<const uint4*>(ep.bias + n0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) add_half8(v + 8 * j, __ldg(bp + j));
+      }
+      if (ACT == kActQuickGelu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = act_quick_gelu(v[j]);
+      } else if (ACT == kActGeluErf) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = act_gelu_erf(v[j]);
+      }
+      if (ACT == kActSwiGLU) {
+        // columns [16g, 16g+8) = gate, [16g+8, 16g+16) = up  ->  8 outputs per granule
+        uint32_t o[8];
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) {
+            const float a = act_silu(v[16 * g + e]) * v[16 * g + 8 + e];
+            const float b = act_silu(v[16 * g + e + 1]) * v[16 * g + 8 + e + 1];
+            o[4 * g + e / 2] = pack_half2(a, b);
+          }
+        }
+        uint4* cp = reinterpret_cast<uint4*>(ep.C + out_row * ep.ldc + (n0 >> 1));
+        cp[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        cp[1] = make_uint4(o[4], o[5], o[6], o[7]);
+      } else {
+        if (ep.residual) {
+          const uint4* rp = reinterpret_cast<const uint4*>(ep.residual + res_row * ep.ldr + n0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) add_half8(v + 8 * j, rp[j]);
+        }
+        uint4* cp = reinterpret_cast<uint4*>(ep.C + out_row * ep.ldc + n0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          cp[j] = make_uint4(pack_half2(v[8 * j + 0], v[8 * j + 1]), pack_half2(v[8 * j + 2], v[8 * j + 3]),
+                             pack_half2(v[8 * j + 4], v[8 * j + 5]), pack_half2(v[8 * j + 6], v[8 * j + 7]));
+        }
+      }
+    }
+  }
 }
 
 template <int BN, int ACT>
@@ -142,64 +208,8 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int tm = tile / tiles_n, tn = tile % tiles_n;
       mbar_wait(bar(2 * S + acc), acc_phase);
       tc_fence_after();
-      const int m = tm * BM + q * 32 + lane;
-      const bool row_ok = m < M;
-      long out_row = m;
-      if (ep.out_group) out_row = m + static_cast<long>(m / ep.out_group) * ep.out_skip + ep.out_off;
-      const long res_row = ep.res_mod ? static_cast<long>(m % ep.res_mod) + ep.res_off : out_row;
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        const int n0 = tn * BN + c;
-        if (n0 >= N) break;
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c, r);
-        tmem_ld_wait();
-        if (row_ok) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (ep.bias) {
-            const uint4* bp = reinterpret_cast<const uint4*>(ep.bias + n0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) add_half8(v + 8 * j, __ldg(bp + j));
-          }
-          if (ACT == kActQuickGelu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = act_quick_gelu(v[j]);
-          } else if (ACT == kActGeluErf) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = act_gelu_erf(v[j]);
-          }
-          if (ACT == kActSwiGLU) {
-            // columns [16g, 16g+8) = gate, [16g+8, 16g+16) = up  ->  8 outputs per granule
-            uint32_t o[8];
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-#pragma unroll
-              for (int e = 0; e < 8; e += 2) {
-                const float a = act_silu(v[16 * g + e]) * v[16 * g + 8 + e];
-                const float b = act_silu(v[16 * g + e + 1]) * v[16 * g + 8 + e + 1];
-                o[4 * g + e / 2] = pack_half2(a, b);
-              }
-            }
-            uint4* cp = reinterpret_cast<uint4*>(ep.C + out_row * ep.ldc + (n0 >> 1));
-            cp[0] = make_uint4(o[0], o[1], o[2], o[3]);
-            cp[1] = make_uint4(o[4], o[5], o[6], o[7]);
-          } else {
-            if (ep.residual) {
-              const uint4* rp = reinterpret_cast<const uint4*>(ep.residual + res_row * ep.ldr + n0);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) add_half8(v + 8 * j, rp[j]);
-            }
-            uint4* cp = reinterpret_cast<uint4*>(ep.C + out_row * ep.ldc + n0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              cp[j] = make_uint4(pack_half2(v[8 * j + 0], v[8 * j + 1]), pack_half2(v[8 * j + 2], v[8 * j + 3]),
-                                 pack_half2(v[8 * j + 4], v[8 * j + 5]), pack_half2(v[8 * j + 6], v[8 * j + 7]));
-            }
-          }
-        }
-      }
+      gemm_epilogue_tile<BN, ACT>(ep, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN, tm * BM + q * 32 + lane, M, N,
+                                  tn * BN);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(2 * S + 2 + acc));
@@ -212,6 +222,144 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+
+// -------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): one 256 x 256 output tile per pair of SMs.  Each CTA stages ITS 128 rows of A and ITS
+// 128 of the tile's 256 W rows (32 KiB per k-block instead of 48), the leader's single MMA thread issues
+// tcgen05.mma.cta_group::2 (M = 256) which reads both CTAs' shared memory and writes each CTA's own TMEM half, and every
+// CTA runs the epilogue of its own 128 rows.  Per SM and k-block the shared-memory traffic drops from 192 B/clk (TMA writes
+// + MMA reads of the 1-CTA 128 x 256 tile) to 128 B/clk, which is what bounds the 1-CTA kernel.
+//   full[s]      (leader only, count 1): leader's producer arrives with expect_tx of BOTH CTAs' stage bytes; both CTAs' TMA
+//                loads complete_tx on it (tma_load_2d_2sm)
+//   empty[s]     (each CTA, count 1): tcgen05.commit multicast from the leader's MMA thread
+//   tmem_full[a] (each CTA, count 1): commit multicast after the tile's last k-block
+//   tmem_empty[a](leader only, count 8): the four epilogue warps of each CTA (the peer's arrive through DSMEM)
+// -------------------------------------------------------------------------------------------------
+struct PairCfg {
+  static constexpr int kStages = 6;
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = 128 * BK * 2;  // this CTA's half of the 256 W rows
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 256 + 1024;
+  static constexpr int kTmemCols = 512;  // two 256-column accumulator buffers
+};
+
+template <int ACT>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc5_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmEpilogue ep,
+                     int M, int N, int K, int tiles_m, int tiles_n) {
+  using Cfg = PairCfg;
+  constexpr int BN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (tiles_addr - raw_addr);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  const uint32_t bars_addr = tiles_addr + Cfg::kStages * Cfg::kStageBytes;
+  auto bar = [&](int i) -> uint32_t { return bars_addr + 8u * static_cast<uint32_t>(i); };
+  constexpr int S = Cfg::kStages;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * S + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs), 1 = peer
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2 * S; ++i) mbar_init(bar(i), 1);
+    mbar_init(bar(2 * S + 0), 1);
+    mbar_init(bar(2 * S + 1), 1);
+    mbar_init(bar(2 * S + 2), 8);
+    mbar_init(bar(2 * S + 3), 8);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(smem_u32(const_cast<uint32_t*>(tmem_slot)), Cfg::kTmemCols);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers exist before anything is signalled across the pair
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_kb = K / BK;
+  const int num_tiles = tiles_m * tiles_n;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      int s = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += n_pairs) {
+        const int tm = tile / tiles_n, tn = tile % tiles_n;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar(S + s), phase ^ 1u);
+          const uint32_t a_dst = tiles_addr + s * Cfg::kStageBytes;
+          if (rank == 0) mbar_expect_tx(bar(s), 2 * Cfg::kStageBytes);
+          tma_load_2d_2sm(a_dst, &tmA, bar(s), kb * BK, tm * 256 + static_cast<int>(rank) * BM);
+          tma_load_2d_2sm(a_dst + Cfg::kABytes, &tmB, bar(s), kb * BK, tn * BN + static_cast<int>(rank) * 128);
+          if (++s == S) { s = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(256, BN);
+      int s = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = pair; tile < num_tiles; tile += n_pairs, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(bar(2 * S + 2 + acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar(s), phase);
+          tc_fence_after();
+          const uint32_t a_addr = tiles_addr + s * Cfg::kStageBytes;
+          const uint64_t adesc = make_sw128_kmajor_desc(a_addr);
+          const uint64_t bdesc = make_sw128_kmajor_desc(a_addr + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_f16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2sm(bar(S + s), 0b11);  // frees the stage in BOTH CTAs
+          if (++s == S) { s = 0; phase ^= 1u; }
+        }
+        umma_commit_2sm(bar(2 * S + acc), 0b11);  // accumulator complete -> both epilogues
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += n_pairs, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int tm = tile / tiles_n, tn = tile % tiles_n;
+      mbar_wait(bar(2 * S + acc), acc_phase);
+      tc_fence_after();
+      gemm_epilogue_tile<BN, ACT>(ep, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN,
+                                  tm * 256 + static_cast<int>(rank) * BM + q * 32 + lane, M, N, tn * BN);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(bar(2 * S + 2 + acc));
+        else mbar_arrive_cluster(dsmem_addr(bar(2 * S + 2 + acc), 0));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // neither CTA frees TMEM or exits while the pair's MMAs / remote arrivals may still touch it
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -285,6 +433,46 @@ int launch_act(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpilogu
   }
 }
 
+
+template <int ACT>
+int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpilogue& ep, int M, int N, int K,
+                cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    VCB_CUDA(cudaFuncSetAttribute(gemm_tc5_pair_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles_m = (M + 255) / 256;
+  const int tiles_n = N / 256;
+  const int pairs = std::min(tiles_m * tiles_n, device_sm_count() / 2);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = PairCfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  KernelScope scope(kCatGemm, stream);
+  VCB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc5_pair_kernel<ACT>, tmA, tmB, ep, M, N, K, tiles_m, tiles_n));
+  return kOk;
+}
+
+int launch_pair_act(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpilogue& ep, int M, int N, int K,
+                    cudaStream_t stream) {
+  switch (ep.act) {
+    case kActNone: return launch_pair<kActNone>(tmA, tmB, ep, M, N, K, stream);
+    case kActQuickGelu: return launch_pair<kActQuickGelu>(tmA, tmB, ep, M, N, K, stream);
+    case kActGeluErf: return launch_pair<kActGeluErf>(tmA, tmB, ep, M, N, K, stream);
+    case kActSwiGLU: return launch_pair<kActSwiGLU>(tmA, tmB, ep, M, N, K, stream);
+    default: set_thread_error("gemm_f16: unknown activation"); return kErrInvalid;
+  }
+}
+
 }  // namespace
 
 // generic 2-D fp16 tensor map with the 128-byte swizzle (box_inner must be 64 elements = 128 bytes)
@@ -346,6 +534,19 @@ int gemm_f16(const __half* A, int lda, const __half* W, int ldw, int M, int N, i
                 (reinterpret_cast<uintptr_t>(ep.C) & 15) == 0,
             kErrInvalid, "gemm_f16: pointers must be 16-byte aligned");
   VCB_CHECK(ep.C != nullptr && ep.ldc % 8 == 0, kErrInvalid, "gemm_f16: bad output");
+  {
+    // block_n == 512 or VCB_GEMM_PAIR=1: CTA-pair kernel (256 x 256 tile per two SMs) where the shape allows it
+    static int env_pair = -1;
+    if (env_pair < 0) { const char* e = getenv("VCB_GEMM_PAIR"); env_pair = e ? atoi(e) : kGemmPairDefault; }
+    const bool want_pair = block_n == 512 || (block_n == 0 && env_pair != 0 && M >= 1024);
+    if (want_pair && N % 256 == 0) {
+      CUtensorMap tmA, tmB;
+      VCB_TRY(make_tmap_kmajor(&tmA, A, K, M, lda, BM));
+      VCB_TRY(make_tmap_kmajor(&tmB, W, K, N, ldw, 128));
+      return launch_pair_act(tmA, tmB, ep, M, N, K, stream);
+    }
+    VCB_CHECK(block_n != 512, kErrInvalid, "gemm_f16: the CTA-pair kernel needs N % 256 == 0");
+  }
   int bn = block_n;
   if (bn == 0) {
     // 256-wide tiles halve the A re-reads; keep 128 when that would leave SMs idle.
