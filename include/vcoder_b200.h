@@ -98,7 +98,8 @@ int vcb_device_count(void);
 
 /* C[M,N] = act(A[M,K] · W[N,K]^T + bias) (+ residual).  Replaces nn.Linear / F.linear on the path.
  * act: 0 none, 1 quick_gelu (CLIP), 2 gelu erf (mm_projector), 3 SwiGLU with 8/8-interleaved gate|up rows
- * (output then has N/2 columns).  block_n: 0 auto, 128, 256. */
+ * (output then has N/2 columns).  block_n: 0 auto, 128 / 256 (tile width of the 1-CTA kernel), 512 (the
+ * CTA-pair kernel: 256 x 256 tile on two SMs with tcgen05 cta_group::2; needs N % 256 == 0). */
 int vcb_op_gemm_f16(const vcb_half* A_dev, int32_t lda, const vcb_half* W_dev, int32_t ldw, int32_t M, int32_t N,
                     int32_t K, const vcb_half* bias_dev, const vcb_half* residual_dev, int32_t ldr, int32_t act,
                     vcb_half* C_dev, int32_t ldc, int32_t block_n, void* stream);

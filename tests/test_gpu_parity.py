@@ -57,6 +57,10 @@ def assert_close_kernel(got, ref, what):
     (128, 128, 64, 0, 0, 0, 128), (300, 384, 640, 0, 1, 0, 128), (300, 512, 640, 1, 1, 1, 256),
     (1000, 1024, 1024, 2, 1, 0, 0), (1000, 1024, 1024, 3, 0, 0, 128), (577 * 3, 3072, 1024, 0, 1, 0, 0),
     (1, 256, 128, 0, 1, 1, 128), (2 * 1207, 4096, 4096, 0, 0, 1, 256),
+    # block_n = 512: the CTA-pair (cta_group::2) kernel, 256 x 256 tile per two SMs
+    (256, 256, 64, 0, 0, 0, 512), (300, 512, 640, 1, 1, 1, 512), (1000, 1024, 1024, 2, 1, 0, 512),
+    (1000, 1024, 1024, 3, 0, 0, 512), (2 * 1207, 4096, 4096, 0, 0, 1, 512), (577 * 3, 3072, 1024, 0, 1, 0, 512),
+    (1, 256, 128, 0, 1, 1, 512), (9656, 1024, 4096, 0, 0, 1, 0),
 ])
 def test_gemm_tc5(M, N, K, act, bias, res, bn):
     lib = _lib.load()

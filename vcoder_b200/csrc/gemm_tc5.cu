@@ -25,7 +25,9 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 fp16 = 128 bytes = one swizzle-128B row
 constexpr int kGemmThreads = 192;
-constexpr int kGemmPairDefault = 0;  // VCB_GEMM_PAIR unset: 1-CTA kernel (see DESIGN.md section 3 for the measurement)
+constexpr int kRasterGroup1 = 16;  // tile rows per band, 1-CTA kernel: minimises 16 x 1 MB (A) + 148/16 x 2 MB (W) per wave at K = 4096
+constexpr int kRasterGroup2 = 8;   // CTA-pair kernel: 8 x 2 MB + 74/8 x 2 MB
+constexpr int kGemmPairDefault = 1;  // VCB_GEMM_PAIR=0 forces the 1-CTA kernel (A/B: DESIGN.md section 3, profiles/r01_gemm_pair_s3.log)
 
 template <int BN>
 struct GemmCfg {
@@ -46,6 +48,20 @@ __device__ __forceinline__ float act_silu(float x) { return __fdividef(x, 1.0f +
 __device__ __forceinline__ void add_half8(float* v, const uint4& h) {
   float2 a = unpack_half2(h.x), b = unpack_half2(h.y), c = unpack_half2(h.z), d = unpack_half2(h.w);
   v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y; v[4] += c.x; v[5] += c.y; v[6] += d.x; v[7] += d.y;
+}
+
+// Tile rasterisation: tiles are walked in bands of kGroup tile rows, column by column inside a band, so the CTAs that run
+// concurrently (one wave = 148 tiles or 74 pair-tiles) cover a squarish block of the output and share A row-blocks AND W
+// column-blocks in L2.  Row-major order made every wave stream its own ~150 MB of W through the 126 MB L2 (ncu: 6.7 GB of
+// DRAM reads for the 9656 x 22016 x 4096 gate|up GEMM against 0.26 GB of operands).
+template <int kGroup>
+__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int* tm, int* tn) {
+  const int band = kGroup * tiles_n;
+  const int first_m = (tile / band) * kGroup;
+  const int rows = min(tiles_m - first_m, kGroup);
+  const int in_band = tile % band;
+  *tm = first_m + in_band % rows;
+  *tn = in_band / rows;
 }
 
 // Epilogue of one accumulator row: `tmem_acc` = TMEM address of this thread's lane at the first column of the accumulator
@@ -158,7 +174,8 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int s = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int tm = tile / tiles_n, tn = tile % tiles_n;
+        int tm, tn;
+        tile_coords<kRasterGroup1>(tile, tiles_m, tiles_n, &tm, &tn);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bar(S + s), phase ^ 1u);
           const uint32_t a_dst = tiles_addr + s * Cfg::kStageBytes;
@@ -205,7 +222,8 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int tm = tile / tiles_n, tn = tile % tiles_n;
+      int tm, tn;
+      tile_coords<kRasterGroup1>(tile, tiles_m, tiles_n, &tm, &tn);
       mbar_wait(bar(2 * S + acc), acc_phase);
       tc_fence_after();
       gemm_epilogue_tile<BN, ACT>(ep, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN, tm * BM + q * 32 + lane, M, N,
@@ -296,7 +314,8 @@ gemm_tc5_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       int s = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += n_pairs) {
-        const int tm = tile / tiles_n, tn = tile % tiles_n;
+        int tm, tn;
+        tile_coords<kRasterGroup2>(tile, tiles_m, tiles_n, &tm, &tn);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bar(S + s), phase ^ 1u);
           const uint32_t a_dst = tiles_addr + s * Cfg::kStageBytes;
@@ -339,7 +358,8 @@ gemm_tc5_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     for (int tile = pair; tile < num_tiles; tile += n_pairs, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int tm = tile / tiles_n, tn = tile % tiles_n;
+      int tm, tn;
+      tile_coords<kRasterGroup2>(tile, tiles_m, tiles_n, &tm, &tn);
       mbar_wait(bar(2 * S + acc), acc_phase);
       tc_fence_after();
       gemm_epilogue_tile<BN, ACT>(ep, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN,
@@ -538,7 +558,10 @@ int gemm_f16(const __half* A, int lda, const __half* W, int ldw, int M, int N, i
     // block_n == 512 or VCB_GEMM_PAIR=1: CTA-pair kernel (256 x 256 tile per two SMs) where the shape allows it
     static int env_pair = -1;
     if (env_pair < 0) { const char* e = getenv("VCB_GEMM_PAIR"); env_pair = e ? atoi(e) : kGemmPairDefault; }
-    const bool want_pair = block_n == 512 || (block_n == 0 && env_pair != 0 && M >= 1024);
+    // measured on B200: +7..18 % on the K >= 4096 prefill shapes, +4..5 % on the K = 1024 tower GEMMs without an activation,
+    // -2 % on the K = 1024 fc1 (quick_gelu) GEMM, which therefore stays on the 1-CTA kernel
+    const bool short_k_act = K < 2048 && ep.act != kActNone;
+    const bool want_pair = block_n == 512 || (block_n == 0 && env_pair != 0 && M >= 1024 && !short_k_act);
     if (want_pair && N % 256 == 0) {
       CUtensorMap tmA, tmB;
       VCB_TRY(make_tmap_kmajor(&tmA, A, K, M, lda, BM));
