@@ -558,10 +558,19 @@ int gemm_f16(const __half* A, int lda, const __half* W, int ldw, int M, int N, i
     // block_n == 512 or VCB_GEMM_PAIR=1: CTA-pair kernel (256 x 256 tile per two SMs) where the shape allows it
     static int env_pair = -1;
     if (env_pair < 0) { const char* e = getenv("VCB_GEMM_PAIR"); env_pair = e ? atoi(e) : kGemmPairDefault; }
-    // measured on B200: +7..18 % on the K >= 4096 prefill shapes, +4..5 % on the K = 1024 tower GEMMs without an activation,
-    // -2 % on the K = 1024 fc1 (quick_gelu) GEMM, which therefore stays on the 1-CTA kernel
+    // measured on B200 (profiles/r01_gemm_pair_s3.log, r01_gemm_raster_s3.log): the pair kernel is 5..10 % faster per tile on
+    // the large shapes, 1-CTA wins on the K = 1024 GEMMs with an activation epilogue and whenever the 256 x 256 tiling
+    // quantises into a worse last wave (e.g. M = 4616: 304 pair-tiles on 74 pairs = 5 rounds vs 592 tiles on 148 SMs = 4)
     const bool short_k_act = K < 2048 && ep.act != kActNone;
-    const bool want_pair = block_n == 512 || (block_n == 0 && env_pair != 0 && M >= 1024 && !short_k_act);
+    bool auto_pair = false;
+    if (block_n == 0 && env_pair != 0 && M >= 1024 && N % 256 == 0 && !short_k_act) {
+      const int sms = device_sm_count();
+      const long t1 = static_cast<long>((M + BM - 1) / BM) * (N / 256), t2 = static_cast<long>((M + 255) / 256) * (N / 256);
+      const double eff1 = static_cast<double>(t1) / (((t1 + sms - 1) / sms) * sms);
+      const double eff2 = static_cast<double>(t2) / (((t2 + sms / 2 - 1) / (sms / 2)) * (sms / 2));
+      auto_pair = eff2 * 1.07 >= eff1;
+    }
+    const bool want_pair = block_n == 512 || auto_pair;
     if (want_pair && N % 256 == 0) {
       CUtensorMap tmA, tmB;
       VCB_TRY(make_tmap_kmajor(&tmA, A, K, M, lda, BM));
