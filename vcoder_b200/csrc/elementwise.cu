@@ -249,6 +249,33 @@ __global__ void embed_gather_kernel(const int32_t* __restrict__ ids, const __hal
 
 // ---- greedy: next = argmax(logits[:, -1]) over fp16 logits, lowest index wins ties (GenerationMixin greedy; K13)
 constexpr int kArgThreads = 256;
+// embedding gather of the decode step + the producer half of layer 0's input RMSNorm (see SkinnyParams::pn_*)
+__global__ void __launch_bounds__(128)
+embed_gather_norm_kernel(const int32_t* __restrict__ ids, const __half* __restrict__ embed, __half* __restrict__ out,
+                         const __half* __restrict__ norm_w, __half* __restrict__ xn_out, float* __restrict__ parts, int H) {
+  __shared__ float scratch[4];
+  griddep_launch();
+  griddep_wait();
+  const int b = blockIdx.x;
+  const uint4* src = reinterpret_cast<const uint4*>(embed + static_cast<long>(ids[b]) * H);
+  const uint4* wq = reinterpret_cast<const uint4*>(norm_w);
+  uint4* o = reinterpret_cast<uint4*>(out + static_cast<long>(b) * H);
+  uint4* on = reinterpret_cast<uint4*>(xn_out + static_cast<long>(b) * H);
+  float sq = 0.f;
+  for (int c = threadIdx.x; c < H / 8; c += blockDim.x) {
+    const uint4 v = __ldg(src + c);
+    o[c] = v;
+    float x[8], w[8], y[8];
+    unpack8(v, x);
+    unpack8(__ldg(wq + c), w);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sq += x[j] * x[j]; y[j] = x[j] * w[j]; }
+    on[c] = pack8(y);
+  }
+  const float tot = block_sum<128>(sq, scratch);
+  if (threadIdx.x == 0) parts[b] = tot;
+}
+
 __global__ void __launch_bounds__(kArgThreads)
 argmax_kernel(const __half* __restrict__ logits, int V, int32_t* next, int32_t* trace, int trace_stride,
               const int32_t* __restrict__ step_dev) {
@@ -353,6 +380,13 @@ int splice_gather(const int32_t* plan, const __half* embed, const __half* feats,
 int embed_gather(const int32_t* ids, const __half* embed, __half* out, int B, int H, cudaStream_t s) {
   KernelScope scope(kCatMisc, s);
   VCB_CUDA(launch_pdl(embed_gather_kernel, dim3(B), dim3(128), 0, s, ids, embed, out, H));
+  return kOk;
+}
+
+int embed_gather_norm(const int32_t* ids, const __half* embed, __half* out, const __half* norm_w, __half* xn_out,
+                      float* parts, int B, int H, cudaStream_t s) {
+  KernelScope scope(kCatMisc, s);
+  VCB_CUDA(launch_pdl(embed_gather_norm_kernel, dim3(B), dim3(128), 0, s, ids, embed, out, norm_w, xn_out, parts, H));
   return kOk;
 }
 

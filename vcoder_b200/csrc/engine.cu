@@ -15,6 +15,7 @@ namespace vcb {
 
 namespace {
 
+constexpr int kNormChainDefault = 1;   // decode step without rmsnorm kernels (VCB_DECODE_NORM_CHAIN=0: separate kernels)
 constexpr bool kPackedDefault = false;  // VCB_SKINNY_PACKED unset: decode streams the row-major weights through the tensor map
 
 int dev_alloc(Engine* e, DevBuf* b, size_t bytes) {
@@ -183,6 +184,14 @@ int engine_create(const vcb_config* c, int device, Engine** out) {
   if (rc == kOk) rc = dev_alloc(e, &e->counters, 16);
   if (rc == kOk) rc = dev_alloc(e, &e->sample_params, 32);
   if (rc == kOk) rc = dev_alloc(e, &e->fp_dev, 8);
+  if (rc == kOk) rc = dev_alloc(e, &e->norm_parts0, 32 * 4);
+  if (rc == kOk) rc = dev_alloc(e, &e->norm_parts_a, static_cast<size_t>(H / 16) * 32 * 4);
+  if (rc == kOk) rc = dev_alloc(e, &e->norm_parts_b, static_cast<size_t>(H / 16) * 32 * 4);
+  if (rc == kOk) {
+    cudaMemset(e->norm_parts0.p, 0, e->norm_parts0.bytes);
+    cudaMemset(e->norm_parts_a.p, 0, e->norm_parts_a.bytes);
+    cudaMemset(e->norm_parts_b.p, 0, e->norm_parts_b.bytes);
+  }
 #undef ALLOC
   if (rc != kOk) { delete e; return rc; }
   if (cudaMallocHost(&e->plan_host, e->max_rows * 4) != cudaSuccess ||
@@ -843,15 +852,30 @@ int decode_step_launch(Engine* e, int max_ctx, cudaStream_t st) {
   static int rope_env = -1;  // RoPE + KV append fused into the decode attention kernel (VCB_FUSE_ROPE=0: separate kernel)
   if (rope_env < 0) { const char* ev = getenv("VCB_FUSE_ROPE"); rope_env = ev ? atoi(ev) : 1; }
   const bool fuse_rope = rope_env != 0;
-  VCB_TRY(embed_gather(e->next_ids.as<int32_t>(), e->embed.as<__half>(), x, B, H, st));
+  // Chained RMSNorm (default): no norm kernel inside the step.  The GEMM that produces the residual stream (o-proj,
+  // down-proj; the embedding gather for layer 0) also emits fp16(x * w_next_norm) and per-CTA partial sum(x^2); the GEMM
+  // that follows (qkv, gate|up, lm_head) scales its accumulators by rsqrt(mean(x^2) + eps).  VCB_DECODE_NORM_CHAIN=0 keeps
+  // the separate rmsnorm kernels (65 more launches per step).
+  static int chain_env = -1;
+  if (chain_env < 0) { const char* ev = getenv("VCB_DECODE_NORM_CHAIN"); chain_env = ev ? atoi(ev) : kNormChainDefault; }
+  const bool chain = chain_env != 0 && !fuse_norm && H % 64 == 0 && FF % 64 == 0;  // the TMA kernel carries the chain
+  float* parts0 = e->norm_parts0.as<float>();
+  float* parts_a = e->norm_parts_a.as<float>();
+  float* parts_b = e->norm_parts_b.as<float>();
+  const int nparts = H / 16;  // CTAs of a GEMM with N = H
+  if (chain)
+    VCB_TRY(embed_gather_norm(e->next_ids.as<int32_t>(), e->embed.as<__half>(), x, e->llm[0].ln1.as<__half>(), xn, parts0, B, H, st));
+  else
+    VCB_TRY(embed_gather(e->next_ids.as<int32_t>(), e->embed.as<__half>(), x, B, H, st));
   for (int li = 0; li < c.llm_layers; ++li) {
     const LlmLayerW& l = e->llm[li];
     __half* kp = e->k_pool.as<__half>() + li * layer_pool;
     __half* vp = e->v_pool.as<__half>() + li * layer_pool;
-    if (!fuse_norm) VCB_TRY(rmsnorm_f16(x, l.ln1.as<__half>(), xn, B, H, c.llm_rms_eps, st));
+    if (!fuse_norm && !chain) VCB_TRY(rmsnorm_f16(x, l.ln1.as<__half>(), xn, B, H, c.llm_rms_eps, st));
     {
       SkinnyParams s;
       if (fuse_norm) { s.norm_w = l.ln1.as<__half>(); s.norm_eps = c.llm_rms_eps; }
+      if (chain) { s.cn_parts = li == 0 ? parts0 : parts_b; s.cn_nparts = li == 0 ? 1 : nparts; s.cn_eps = c.llm_rms_eps; }
       s.X = fuse_norm ? x : xn; s.ldx = H; s.W = l.qkv_w.as<__half>(); s.Wp = l.qkv_p.as<__half>(); s.Y = qkv; s.ldy = 3 * H; s.B = B; s.N = 3 * H; s.K = H;
       VCB_TRY(skinny_gemm(s, st));
     }
@@ -873,12 +897,14 @@ int decode_step_launch(Engine* e, int max_ctx, cudaStream_t st) {
       SkinnyParams s;
       s.X = e->attnd.as<__half>(); s.ldx = H; s.W = l.o_w.as<__half>(); s.Wp = l.o_p.as<__half>(); s.Y = x; s.ldy = H; s.residual = x; s.ldr = H;
       s.B = B; s.N = H; s.K = H;
+      if (chain) { s.pn_w = l.ln2.as<__half>(); s.pn_out = xn; s.pn_ld = H; s.pn_parts = parts_a; }
       VCB_TRY(skinny_gemm(s, st));
     }
-    if (!fuse_norm) VCB_TRY(rmsnorm_f16(x, l.ln2.as<__half>(), xn, B, H, c.llm_rms_eps, st));
+    if (!fuse_norm && !chain) VCB_TRY(rmsnorm_f16(x, l.ln2.as<__half>(), xn, B, H, c.llm_rms_eps, st));
     {
       SkinnyParams s;
       if (fuse_norm) { s.norm_w = l.ln2.as<__half>(); s.norm_eps = c.llm_rms_eps; }
+      if (chain) { s.cn_parts = parts_a; s.cn_nparts = nparts; s.cn_eps = c.llm_rms_eps; }
       s.X = fuse_norm ? x : xn; s.ldx = H; s.W = l.gu_w.as<__half>(); s.Wp = l.gu_p.as<__half>(); s.Y = e->midd.as<__half>(); s.ldy = FF; s.B = B; s.N = 2 * FF;
       s.K = H; s.swiglu = 1;
       VCB_TRY(skinny_gemm(s, st));
@@ -887,13 +913,18 @@ int decode_step_launch(Engine* e, int max_ctx, cudaStream_t st) {
       SkinnyParams s;
       s.X = e->midd.as<__half>(); s.ldx = FF; s.W = l.down_w.as<__half>(); s.Wp = l.down_p.as<__half>(); s.Y = x; s.ldy = H; s.residual = x; s.ldr = H;
       s.B = B; s.N = H; s.K = FF;
+      if (chain) {
+        s.pn_w = (li + 1 < c.llm_layers ? e->llm[li + 1].ln1 : e->final_norm).as<__half>();
+        s.pn_out = xn; s.pn_ld = H; s.pn_parts = parts_b;
+      }
       VCB_TRY(skinny_gemm(s, st));
     }
   }
-  if (!fuse_norm) VCB_TRY(rmsnorm_f16(x, e->final_norm.as<__half>(), xn, B, H, c.llm_rms_eps, st));
+  if (!fuse_norm && !chain) VCB_TRY(rmsnorm_f16(x, e->final_norm.as<__half>(), xn, B, H, c.llm_rms_eps, st));
   {
     SkinnyParams s;
     if (fuse_norm) { s.norm_w = e->final_norm.as<__half>(); s.norm_eps = c.llm_rms_eps; }
+    if (chain) { s.cn_parts = parts_b; s.cn_nparts = nparts; s.cn_eps = c.llm_rms_eps; }
     s.X = fuse_norm ? x : xn; s.ldx = H; s.W = e->lm_head.as<__half>(); s.Wp = e->lm_head_p.as<__half>(); s.Y = e->logits.as<__half>(); s.ldy = V; s.B = B; s.N = V; s.K = H;
     VCB_TRY(skinny_gemm(s, st));
   }

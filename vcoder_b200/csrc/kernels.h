@@ -77,6 +77,18 @@ struct SkinnyParams {
   // fused LlamaRMSNorm on X (decode): Y = rsqrt(mean(x^2)+eps) * W (x o norm_w); null = X is used as is
   const __half* norm_w = nullptr;
   float norm_eps = 0.f;
+  // RMSNorm chained through the GEMMs of a decode step (no norm kernel in between), TMA kernel only:
+  //  producer side (o-proj / down-proj, Y = new residual stream x): also emits the NEXT norm's weighted input
+  //    pn_out[b, c] = fp16(x[b, c] * pn_w[c]) and this CTA's share of sum(x^2): pn_parts[blockIdx.x * 32 + b]
+  //  consumer side (qkv / gate|up / lm_head): X is such a weighted input; the accumulators are scaled by
+  //    rsqrt(sum over cn_nparts partial sums / K + cn_eps) in the epilogue (summed in a fixed order: deterministic)
+  const __half* pn_w = nullptr;
+  __half* pn_out = nullptr;
+  long pn_ld = 0;
+  float* pn_parts = nullptr;
+  const float* cn_parts = nullptr;
+  int cn_nparts = 0;
+  float cn_eps = 0.f;
 };
 int skinny_gemm(const SkinnyParams& p, cudaStream_t stream);
 int skinny_gemm_tma(const SkinnyParams& p, cudaStream_t stream);  // TMA / bulk-copy fed kernel (skinny_tma.cu); needs K % 64 == 0
@@ -98,6 +110,9 @@ int rope_kv_write(__half* qkv, int B, int T, int H, int n_heads, const float2* c
 int splice_gather(const int32_t* plan, const __half* embed, const __half* feats, __half* out, long rows, int H,
                   cudaStream_t s);
 int embed_gather(const int32_t* ids, const __half* embed, __half* out, int B, int H, cudaStream_t s);
+// embed_gather + the first RMSNorm's producer half: out = embed[ids], xn_out = fp16(out * norm_w), parts[b] = sum(out[b]^2)
+int embed_gather_norm(const int32_t* ids, const __half* embed, __half* out, const __half* norm_w, __half* xn_out,
+                      float* parts, int B, int H, cudaStream_t s);
 // first-index argmax over fp16 logits [B,V]; writes next[b] and (optionally) trace[b*trace_stride + *step]
 int argmax_rows(const __half* logits, int B, int V, int32_t* next, int32_t* trace, int trace_stride,
                 const int32_t* step_dev, cudaStream_t s);

@@ -166,6 +166,22 @@ skinny_tma_kernel(const __grid_constant__ CUtensorMap tmW, SkinnyParams p) {
 
   uint4 xv[2 * kGroup][NB], xnext[2 * kGroup][NB];
   if (my_groups > 0) load_x(0, xv);
+  // chained RMSNorm, consumer half: every thread sums a fixed subset of the producer CTAs' partial sum(x^2) — the loads
+  // travel together with the first X fragments
+  float cn[8 * NB];
+#pragma unroll
+  for (int j = 0; j < 8 * NB; ++j) cn[j] = 0.f;
+  const bool chain_in = p.cn_parts != nullptr;
+  if (chain_in) {
+    for (int part = tid; part < p.cn_nparts; part += WARPS * 32) {
+      const float4* q = reinterpret_cast<const float4*>(p.cn_parts + static_cast<long>(part) * 32);
+#pragma unroll
+      for (int j = 0; j < 2 * NB; ++j) {
+        const float4 v = q[j];
+        cn[4 * j] += v.x; cn[4 * j + 1] += v.y; cn[4 * j + 2] += v.z; cn[4 * j + 3] += v.w;
+      }
+    }
+  }
   for (int i = 0; i < my_groups; ++i) {
     const int s = i % kDepth;
     const uint32_t ph = static_cast<uint32_t>((i / kDepth) & 1);
@@ -225,14 +241,23 @@ skinny_tma_kernel(const __grid_constant__ CUtensorMap tmW, SkinnyParams p) {
       v += __shfl_xor_sync(0xffffffffu, v, 2);
       if (t == 0) s_ssq[warp * 8 * NB + nb * 8 + g] = v;
     }
+  } else if (chain_in) {
+#pragma unroll
+    for (int j = 0; j < 8 * NB; ++j) {
+      float v = cn[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) s_ssq[warp * 8 * NB + j] = v;
+    }
   }
   __syncthreads();
+  const float norm_eps = fuse_norm ? p.norm_eps : p.cn_eps;
   auto rstd_of = [&](int n) -> float {
-    if (!fuse_norm) return 1.f;
+    if (!fuse_norm && !chain_in) return 1.f;
     float v = 0.f;
 #pragma unroll
     for (int w = 0; w < WARPS; ++w) v += s_ssq[w * 8 * NB + n];
-    return rsqrtf(v / static_cast<float>(p.K) + p.norm_eps);
+    return rsqrtf(v / static_cast<float>(p.K) + norm_eps);
   };
   constexpr int kThreads = WARPS * 32;
   if (p.swiglu) {
@@ -249,15 +274,32 @@ skinny_tma_kernel(const __grid_constant__ CUtensorMap tmW, SkinnyParams p) {
       }
     }
   } else {
-    for (int idx = tid; idx < 16 * 8 * NB; idx += kThreads) {
+    const bool chain_out = p.pn_parts != nullptr;
+    const float pn_wr = chain_out ? __half2float(p.pn_w[row0 + (tid & 15)]) : 0.f;  // idx & 15 == tid & 15: kThreads % 16 == 0
+    for (int idx = tid; idx < 16 * 8 * NB; idx += kThreads) {  // every iteration is taken by all threads or by none
       const int r = idx & 15, n = idx >> 4;
+      float sq = 0.f;
       if (n < p.B) {
         float v = 0.f;
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) v += red[w][r][n];
         v *= rstd_of(n);
         if (p.residual) v += __half2float(p.residual[static_cast<long>(n) * p.ldr + row0 + r]);
-        p.Y[static_cast<long>(n) * p.ldy + row0 + r] = __float2half_rn(v);
+        const __half h = __float2half_rn(v);
+        p.Y[static_cast<long>(n) * p.ldy + row0 + r] = h;
+        if (chain_out) {
+          // chained RMSNorm, producer half: the norm sees the fp16 residual stream, exactly like the separate kernel
+          const float xv = __half2float(h);
+          sq = xv * xv;
+          p.pn_out[static_cast<long>(n) * p.pn_ld + row0 + r] = __float2half_rn(xv * pn_wr);
+        }
+      }
+      if (chain_out) {  // sum over this CTA's 16 columns: the 16 lanes that share n
+        sq += __shfl_xor_sync(0xffffffffu, sq, 8);
+        sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+        sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+        sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+        if (r == 0 && n < 32) p.pn_parts[static_cast<long>(blockIdx.x) * 32 + n] = sq;
       }
     }
   }
