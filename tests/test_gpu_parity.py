@@ -375,10 +375,10 @@ def test_engine_with_packed_weight_stream_matches_row_major(monkeypatch):
 
 
 def test_decode_norm_chain_matches_separate_rmsnorm_kernels(monkeypatch):
-    """VCB_DECODE_NORM_CHAIN (default on): the decode step has no rmsnorm kernels — the producing GEMM emits fp16(x * w) and
-    partial sum(x^2), the consuming GEMM scales its accumulators by rstd.  Same maths with one rounding placed differently
-    (fp16(x*w) instead of fp16(fp16(x*rstd)*w)): logits agree with the separate-kernel step to fp16 round-off, and with the
-    oracle within the engine tolerance (every other engine test runs with the chain on)."""
+    """VCB_DECODE_NORM_CHAIN=1 (opt-in; measured slower): the decode step has no rmsnorm kernels — the
+    producing GEMM emits fp16(x * w) and partial sum(x^2), the consuming GEMM scales its accumulators by rstd.  Same maths
+    with one rounding placed differently (fp16(x*w) instead of fp16(fp16(x*rstd)*w)): logits agree with the separate-kernel
+    step to fp16 round-off."""
     g = synth.PRESETS["tiny"].with_variant(synth.VARIANT_VCODER_DS)
     sd = synth.make_state_dict(g, seed=0)
     ids = synth.make_prompt_ids(g, 2, seed=4, n_before=6, n_after=5)

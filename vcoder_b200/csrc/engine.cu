@@ -15,7 +15,7 @@ namespace vcb {
 
 namespace {
 
-constexpr int kNormChainDefault = 1;   // decode step without rmsnorm kernels (VCB_DECODE_NORM_CHAIN=0: separate kernels)
+constexpr int kNormChainDefault = 0;   // VCB_DECODE_NORM_CHAIN=1: decode step without rmsnorm kernels (measured slower: DESIGN.md 3.1)
 constexpr bool kPackedDefault = false;  // VCB_SKINNY_PACKED unset: decode streams the row-major weights through the tensor map
 
 int dev_alloc(Engine* e, DevBuf* b, size_t bytes) {
@@ -852,10 +852,11 @@ int decode_step_launch(Engine* e, int max_ctx, cudaStream_t st) {
   static int rope_env = -1;  // RoPE + KV append fused into the decode attention kernel (VCB_FUSE_ROPE=0: separate kernel)
   if (rope_env < 0) { const char* ev = getenv("VCB_FUSE_ROPE"); rope_env = ev ? atoi(ev) : 1; }
   const bool fuse_rope = rope_env != 0;
-  // Chained RMSNorm (default): no norm kernel inside the step.  The GEMM that produces the residual stream (o-proj,
-  // down-proj; the embedding gather for layer 0) also emits fp16(x * w_next_norm) and per-CTA partial sum(x^2); the GEMM
-  // that follows (qkv, gate|up, lm_head) scales its accumulators by rsqrt(mean(x^2) + eps).  VCB_DECODE_NORM_CHAIN=0 keeps
-  // the separate rmsnorm kernels (65 more launches per step).
+  // Chained RMSNorm (VCB_DECODE_NORM_CHAIN=1, off by default): no norm kernel inside the step.  The GEMM that produces the
+  // residual stream (o-proj, down-proj; the embedding gather for layer 0) also emits fp16(x * w_next_norm) and per-CTA
+  // partial sum(x^2); the GEMM that follows (qkv, gate|up, lm_head) scales its accumulators by rsqrt(mean(x^2) + eps).
+  // Parity-green, but measured SLOWER than the 65 separate rmsnorm kernels (4.30 vs 4.05 ms per step): those overlap with
+  // their neighbours through programmatic dependent launch, the extra work inside the GEMMs sits on the critical path.
   static int chain_env = -1;
   if (chain_env < 0) { const char* ev = getenv("VCB_DECODE_NORM_CHAIN"); chain_env = ev ? atoi(ev) : kNormChainDefault; }
   const bool chain = chain_env != 0 && !fuse_norm && H % 64 == 0 && FF % 64 == 0;  // the TMA kernel carries the chain
