@@ -56,7 +56,7 @@ __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* m, int c0, in
 // one contiguous 32*K-byte run of 2 KiB blocks [k-block][16 rows][128 B, chunks pre-swizzled], so a stage is ONE linear
 // 8 KiB bulk copy and every DRAM page the stream touches is consumed completely (the row-major source gives 512-byte runs
 // at an 8 KiB stride).
-template <int NB, int WARPS, int kDepth, int kGroup, bool PACKED>
+template <int NB, int WARPS, int kDepth, int kGroup, bool PACKED, bool CHAIN>
 __global__ void __launch_bounds__(WARPS * 32)
 skinny_tma_kernel(const __grid_constant__ CUtensorMap tmW, SkinnyParams p) {
   constexpr int kStageBytes = kGroup * 16 * kKBlk * 2;  // kGroup k-blocks x 16 rows x 128 B
@@ -168,10 +168,10 @@ skinny_tma_kernel(const __grid_constant__ CUtensorMap tmW, SkinnyParams p) {
   if (my_groups > 0) load_x(0, xv);
   // chained RMSNorm, consumer half: every thread sums a fixed subset of the producer CTAs' partial sum(x^2) — the loads
   // travel together with the first X fragments
-  float cn[8 * NB];
+  float cn[CHAIN ? 8 * NB : 1];
 #pragma unroll
-  for (int j = 0; j < 8 * NB; ++j) cn[j] = 0.f;
-  const bool chain_in = p.cn_parts != nullptr;
+  for (int j = 0; j < (CHAIN ? 8 * NB : 1); ++j) cn[j] = 0.f;
+  const bool chain_in = CHAIN && p.cn_parts != nullptr;  // CHAIN = false: the instantiation every other caller gets
   if (chain_in) {
     for (int part = tid; part < p.cn_nparts; part += WARPS * 32) {
       const float4* q = reinterpret_cast<const float4*>(p.cn_parts + static_cast<long>(part) * 32);
@@ -243,7 +243,7 @@ skinny_tma_kernel(const __grid_constant__ CUtensorMap tmW, SkinnyParams p) {
     }
   } else if (chain_in) {
 #pragma unroll
-    for (int j = 0; j < 8 * NB; ++j) {
+    for (int j = 0; j < (CHAIN ? 8 * NB : 1); ++j) {
       float v = cn[j];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -274,7 +274,7 @@ skinny_tma_kernel(const __grid_constant__ CUtensorMap tmW, SkinnyParams p) {
       }
     }
   } else {
-    const bool chain_out = p.pn_parts != nullptr;
+    const bool chain_out = CHAIN && p.pn_parts != nullptr;
     const float pn_wr = chain_out ? __half2float(p.pn_w[row0 + (tid & 15)]) : 0.f;  // idx & 15 == tid & 15: kThreads % 16 == 0
     for (int idx = tid; idx < 16 * 8 * NB; idx += kThreads) {  // every iteration is taken by all threads or by none
       const int r = idx & 15, n = idx >> 4;
@@ -305,17 +305,17 @@ skinny_tma_kernel(const __grid_constant__ CUtensorMap tmW, SkinnyParams p) {
   }
 }
 
-template <int NB, int WARPS, int kDepth, int kGroup, bool PACKED = false>
+template <int NB, int WARPS, int kDepth, int kGroup, bool PACKED = false, bool CHAIN = false>
 int launch_tma(const CUtensorMap& tm, const SkinnyParams& p, int grid, cudaStream_t stream) {
   constexpr int kStageBytes = kGroup * 16 * kKBlk * 2;
   constexpr int smem = WARPS * kDepth * kStageBytes + WARPS * 16 * (8 * NB + 1) * 4 + 8 + WARPS * kDepth * 8 + WARPS * 8 * NB * 4 + 16;
   static_assert(smem <= 227 * 1024, "skinny_tma: ring does not fit in shared memory");
   static bool attr = false;
   if (!attr) {
-    VCB_CUDA(cudaFuncSetAttribute(skinny_tma_kernel<NB, WARPS, kDepth, kGroup, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    VCB_CUDA(cudaFuncSetAttribute(skinny_tma_kernel<NB, WARPS, kDepth, kGroup, PACKED, CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr = true;
   }
-  VCB_CUDA(launch_pdl(skinny_tma_kernel<NB, WARPS, kDepth, kGroup, PACKED>, dim3(grid), dim3(WARPS * 32), smem, stream, tm, p));
+  VCB_CUDA(launch_pdl(skinny_tma_kernel<NB, WARPS, kDepth, kGroup, PACKED, CHAIN>, dim3(grid), dim3(WARPS * 32), smem, stream, tm, p));
   return kOk;
 }
 // packed weight stream: the measured-best ring shape (4 warps x 2 stages x 8 KiB), or 3 stages (VCB_SKINNY_TMA_DEPTH=3)
@@ -323,6 +323,7 @@ template <int NB>
 int launch_packed(const SkinnyParams& p, int grid, int depth, cudaStream_t stream) {
   CUtensorMap unused;
   memset(&unused, 0, sizeof(unused));
+  if (p.pn_parts != nullptr || p.cn_parts != nullptr) return launch_tma<NB, 4, 2, 4, true, true>(unused, p, grid, stream);
   if (depth >= 3) return launch_tma<NB, 4, 3, 4, true>(unused, p, grid, stream);
   return launch_tma<NB, 4, 2, 4, true>(unused, p, grid, stream);
 }
@@ -342,6 +343,8 @@ __global__ void pack_skinny_kernel(const uint4* __restrict__ W, uint4* __restric
 template <int NB>
 int launch_tma_w(const CUtensorMap& tm, const SkinnyParams& p, int grid, int warps, int depth, int group,
                  cudaStream_t stream) {
+  // the chained RMSNorm (opt-in experiment) exists for the default ring shape only
+  if (p.pn_parts != nullptr || p.cn_parts != nullptr) return launch_tma<NB, 4, 2, 4, false, true>(tm, p, grid, stream);
   if (group == 2) {
     if (depth <= 2) return launch_tma<NB, 4, 2, 2>(tm, p, grid, stream);
     if (depth == 3) return launch_tma<NB, 4, 3, 2>(tm, p, grid, stream);
@@ -405,6 +408,7 @@ int skinny_gemm_tma(const SkinnyParams& p_in, cudaStream_t stream) {
   if (env_d < 0) { const char* e = getenv("VCB_SKINNY_TMA_DEPTH"); env_d = e ? atoi(e) : 0; }
   if (env_w == 2 || env_w == 4 || env_w == 8) warps = env_w;
   if (env_d > 0) depth = env_d;
+  if (p.pn_parts != nullptr || p.cn_parts != nullptr) group = 4;
   CUtensorMap tm;
   VCB_TRY(make_tmap_w3d(&tm, p.W, p.K, p.N, group));
   KernelScope scope(kCatSkinny, stream);
