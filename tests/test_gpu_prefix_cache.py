@@ -90,6 +90,50 @@ def test_multi_turn_reuses_visual_and_generated_tokens():
     assert torch.equal(pre3["next_ids"], pre2["next_ids"])
 
 
+def test_second_turn_against_the_reference_fixture():
+    """The reference's own two-turn run (tests/golden/tiny_ds_turn2.npz, written by tools/make_golden.py --multi-turn: no
+    cache, full recompute per turn) vs the product with the prefix cache on."""
+    import os
+    import numpy as np
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "tiny_ds_turn2.npz"))
+    g = synth.PRESETS["tiny"].with_variant(synth.VARIANT_VCODER_DS)
+    sd = synth.make_state_dict(g, seed=0)
+    assert synth.state_dict_digest(sd) == str(z["weights_digest"])
+    px = [synth.make_pixels(g, 2, s) for s in (1, 2, 3)]
+    eng = Engine(g, max_batch=2, max_seq_len=192)
+    eng.bind(sd)
+    ids1, ids2 = torch.from_numpy(z["ids1"]), torch.from_numpy(z["ids2"])
+    n1, n2 = z["answer1"].shape[1], z["answer2"].shape[1]
+
+    def run_turn(ids, n, ref_ids, ref_logits):
+        pre = eng.prefill(ids, *px, want_logits=True, reuse=True)
+        dec, dec_logits = eng.decode(n - 1, want_logits=True)
+        torch.cuda.synchronize()
+        got = torch.cat([pre["next_ids"][:, None], dec], dim=1).cpu().long()
+        logits = [pre["logits"]] + [dec_logits[s] for s in range(n - 1)]
+        alive = torch.ones(2, dtype=torch.bool)
+        for s in range(n):
+            rl = torch.from_numpy(ref_logits[s])
+            err = (logits[s].float().cpu() - rl).abs().max(dim=-1).values
+            assert bool((err[alive] <= 3e-2).all()), (s, err.tolist())
+            top2 = rl.topk(2, dim=-1).values
+            same = got[:, s] == torch.from_numpy(ref_ids[:, s])
+            assert not bool((alive & ~same & ((top2[:, 0] - top2[:, 1]) > 6e-2)).any()), (s, got[:, s].tolist(), ref_ids[:, s].tolist())
+            alive &= same
+        return pre, got
+
+    pre1, got1 = run_turn(ids1, n1, z["answer1"], z["logits1"])
+    assert pre1["spliced_len"] == int(z["spliced_len1"]) and pre1["reused_len"] == 0 and not pre1["towers_skipped"]
+    pre2, _ = run_turn(ids2, n2, z["answer2"], z["logits2"])
+    assert pre2["spliced_len"] == int(z["spliced_len2"]) and pre2["towers_skipped"]
+    # what is reusable: the turn-1 prompt plus as many of the n1-1 fed-back tokens as agree with the answer the fixture's
+    # turn-2 prompt contains (all of them unless a near-tie flipped a token on the GPU)
+    fed = got1[:, : n1 - 1]
+    ref = torch.from_numpy(z["answer1"])[:, : n1 - 1]
+    agree = min(int((fed[b] == ref[b]).long().cumprod(0).sum()) for b in range(2))
+    assert pre2["reused_len"] == int(z["spliced_len1"]) + agree
+
+
 def test_new_images_only_reuse_the_text_before_them():
     B = 2
     g, sd, ids, px, eng = _setup(B)

@@ -143,3 +143,23 @@ def test_vcoder_it_zero_seg_and_missing_seg_token(golden_dir):
     assert p == [("text", [1]), ("image", 0), ("seg", 0), ("text", [9])]  # the 7 before <seg> is dropped, as in DS
     p = orc.splice_plan([[1, I, 7, 9]], False, False, None, variant=orc.V_LLAVA)[0]
     assert p == [("text", [1]), ("image", 0), ("text", [7, 9])]
+
+
+def test_multi_turn_second_turn(golden_dir):
+    """f3: the reference's own second turn (whole conversation re-sent: turn-1 prompt + its answer + a new message, same
+    images) — the full-recompute result the prefix cache of the product must reproduce (tests/test_gpu_prefix_cache.py)."""
+    z = np.load(os.path.join(golden_dir, "tiny_ds_turn2.npz"))
+    g = synth.PRESETS["tiny"].with_variant(synth.VARIANT_VCODER_DS)
+    sd = synth.make_state_dict(g, seed=0)
+    assert synth.state_dict_digest(sd) == str(z["weights_digest"])
+    z1 = np.load(os.path.join(golden_dir, "tiny_ds.npz"))
+    assert np.array_equal(z["ids1"], z1["ids"]) and np.array_equal(z["answer1"], z1["greedy_ids"])  # turn 1 = the a-row fixture
+    assert np.array_equal(z["ids2"][:, : z["ids1"].shape[1] + z["answer1"].shape[1]], np.concatenate([z["ids1"], z["answer1"]], axis=1))
+    px = [synth.make_pixels(g, 2, s) for s in (1, 2, 3)]
+    n2 = z["answer2"].shape[1]
+    ids_new, trace = orc.greedy_generate(torch.from_numpy(z["ids2"]), sd, g, *px, max_new_tokens=n2, return_logits=True)
+    assert np.array_equal(ids_new.numpy(), z["answer2"])
+    for s, lg in enumerate(trace):
+        _close(lg, z["logits2"][s], atol=5e-4)
+    # F5: two blocks of visual tokens, the depth block dropped; the answer and the follow-up are plain text rows
+    assert int(z["spliced_len2"]) == int(z["spliced_len1"]) + z["answer1"].shape[1] + 7

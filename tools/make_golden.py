@@ -169,6 +169,50 @@ def run_variant(g, out_path, batch=2, n_new=6, seed=0, zero_seg_rows=(), ids=Non
         print("  greedy:", new_ids.tolist())
 
 
+@torch.no_grad()
+def multi_turn_fixture(g, out_path, n1=6, n2=5, seed=0):
+    """SURVEY §8 f3 known answers: what the reference produces on the SECOND turn of a conversation, where the callers
+    (serve/chat.py:41-159, the serve/cli.py loop) re-send the whole conversation — turn-1 prompt + turn-1 answer + the new
+    user message — and all images.  The reference has no cache across generate() calls, so its turn 2 is a full run."""
+    sd = synth.make_state_dict(g, seed=seed)
+    with tempfile.TemporaryDirectory() as td:
+        model = build_reference_model(g, sd, td)
+        images = synth.make_pixels(g, 2, 1).float()
+        segs = synth.make_pixels(g, 2, 2).float()
+        depths = synth.make_pixels(g, 2, 3).float()
+
+        def greedy(ids, n):
+            gen = model.generate(ids, images=images, segs=segs, depths=depths, do_sample=False, use_cache=False,
+                                 max_new_tokens=n, pad_token_id=0, eos_token_id=None)[:, ids.shape[1]:]
+            mask = torch.ones_like(ids)
+            _, _, _, embeds, _ = model.prepare_inputs_labels_for_multimodal(ids, mask, None, None, images, segs, depths)
+            o = model.model(inputs_embeds=embeds, use_cache=True)
+            past = o.past_key_values
+            lg = model.lm_head(o.last_hidden_state)[:, -1]
+            logits, new = [lg.numpy()], [lg.argmax(-1)]
+            for _ in range(n - 1):
+                o = model.model(input_ids=new[-1][:, None], past_key_values=past, use_cache=True)
+                past = o.past_key_values
+                lg = model.lm_head(o.last_hidden_state)[:, -1]
+                logits.append(lg.numpy())
+                new.append(lg.argmax(-1))
+            new = torch.stack(new, dim=1)
+            assert torch.equal(gen, new), (gen, new)
+            return new, np.stack(logits), embeds.shape[1]
+
+        ids1 = synth.make_prompt_ids(g, 2, seed=seed, n_before=5, n_after=4)
+        a1, l1, t1 = greedy(ids1, n1)
+        follow = torch.randint(3, g.llm_vocab, (2, 7), generator=torch.Generator().manual_seed(9))
+        ids2 = torch.cat([ids1, a1, follow], dim=1)
+        a2, l2, t2 = greedy(ids2, n2)
+        out = {"weights_digest": np.array(synth.state_dict_digest(sd)), "ids1": ids1.numpy(), "answer1": a1.numpy(),
+               "logits1": l1, "spliced_len1": np.array(t1), "ids2": ids2.numpy(), "answer2": a2.numpy(), "logits2": l2,
+               "spliced_len2": np.array(t2)}
+        np.savez_compressed(out_path, **out)
+        print(out_path, {k: getattr(v, "shape", None) for k, v in out.items()})
+        print("  turn 1:", a1.tolist(), " turn 2:", a2.tolist())
+
+
 def tokenizer_order_fixture(out_path):
     """F5 known-answer: special-token order emitted by the reference tokenizer helpers (mm_utils.py:43-117)."""
     class Tok:
@@ -216,6 +260,9 @@ if __name__ == "__main__":
     gold = os.path.join(ROOT, "tests", "golden")
     os.makedirs(gold, exist_ok=True)
     torch.manual_seed(0)
+    if "--multi-turn" in sys.argv:  # f3 fixture alone (the others stay byte-identical)
+        multi_turn_fixture(synth.PRESETS["tiny"].with_variant(synth.VARIANT_VCODER_DS), os.path.join(gold, "tiny_ds_turn2.npz"))
+        sys.exit(0)
     only_new = "--only-new" in sys.argv  # keep the committed a-row fixtures byte-identical
     if not only_new:
         run_variant(synth.PRESETS["tiny"].with_variant(synth.VARIANT_VCODER_DS), os.path.join(gold, "tiny_ds.npz"))
@@ -230,3 +277,4 @@ if __name__ == "__main__":
     g_it = synth.PRESETS["tiny"].with_variant(synth.VARIANT_VCODER_IT)
     run_variant(g_it, os.path.join(gold, "tiny_it_noseg.npz"), zero_seg_rows=(0,),
                 ids=synth.make_prompt_ids(g_it, 2, seed=0, n_before=5, n_after=4, specials=[synth.IMAGE_TOKEN_INDEX]))
+    multi_turn_fixture(synth.PRESETS["tiny"].with_variant(synth.VARIANT_VCODER_DS), os.path.join(gold, "tiny_ds_turn2.npz"))
