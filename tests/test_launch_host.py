@@ -234,3 +234,46 @@ def test_reference_eval_model_runs_unmodified(rig):
     assert [int(t) for t in pre[0][1][0] if t < 0] == [I, D, S]
     # batch_decode(skip_special_tokens=True) of [11, 12, 13, </s>]
     assert f"<<ANSWER>>: {rig.tok.decode([11, 12, 13])}\n" in text
+
+
+def test_reference_chat_generate_stream_runs_unmodified(rig):
+    """serve/chat.py:41-159 (the Gradio worker's `Chat.generate_stream`): base64 images in, `model.generate(inputs=...,
+    do_sample, temperature, top_p, streamer=TextIteratorStreamer, stopping_criteria)` — two turns with the same images."""
+    import base64
+    import io
+    import logging
+    from PIL import Image
+    rig.launch.install(REFERENCE)
+    import vcoder_llava.serve.chat as chat
+    assert chat.load_pretrained_model.__module__ == "vcoder_b200.builder"
+
+    def b64(colour):
+        buf = io.BytesIO()
+        Image.new("RGB", (48, 40), colour).save(buf, format="PNG")
+        return base64.b64encode(buf.getvalue()).decode()
+
+    c = chat.Chat(rig.model_dir, None, None, False, False, "cuda", logging.getLogger("test"))
+    assert c.is_multimodal and c.is_seg and c.is_depth
+    imgs, segs, deps = [b64((200, 0, 0))], [b64((0, 200, 0))], [b64((50, 50, 50))]
+    p1 = "USER: <depth>\n<seg>\n<image>\nwhat is this ? ASSISTANT:"
+    params = {"prompt": p1, "images": imgs, "segs": segs, "depths": deps, "temperature": 0.2, "top_p": 0.7,
+              "max_new_tokens": 16, "stop": "</s>"}
+    outs = [json.loads(chunk.decode().rstrip("\0")) for chunk in c.generate_stream(params)]
+    assert outs and all(o["error_code"] == 0 for o in outs)
+    answer = rig.tok.decode([11, 12, 13])
+    assert outs[-1]["text"].startswith(p1) and answer in outs[-1]["text"]
+    eng = FakeEngine.instances[-1]
+    assert ("set_sampling", True, 0.2, 50, 0.7) in eng.calls  # do_sample since temperature > 0.001; top_p forwarded
+    pre = [x for x in eng.calls if x[0] == "prefill"]
+    assert len(pre) == 1 and pre[0][2] and pre[0][3] and pre[0][4] and pre[0][5]
+    assert [int(t) for t in pre[0][1][0] if t < 0] == [I, D, S]
+    # second turn: whole conversation + the same base64 images again (what the prefix cache is for)
+    params["prompt"] = outs[-1]["text"] + "</s>USER: and now ? ASSISTANT:"
+    outs2 = [json.loads(chunk.decode().rstrip("\0")) for chunk in c.generate_stream(params)]
+    assert outs2[-1]["error_code"] == 0
+    pre = [x for x in eng.calls if x[0] == "prefill"]
+    assert len(pre) == 2 and pre[1][1].shape[1] > pre[0][1].shape[1] and pre[1][5]
+    # greedy when temperature <= 0.001
+    params["temperature"] = 0.0
+    list(c.generate_stream(params))
+    assert eng.calls[-3][0] == "set_sampling" and eng.calls[-3][1] is False
