@@ -105,12 +105,12 @@ class FakeEngine:
         return torch.tensor([row] * ids.shape[0], dtype=torch.int64)
 
 
-def _write_checkpoint(root, g):
+def _write_checkpoint(root, g, name="vcoder_ds_llava-tiny"):
     from safetensors.torch import save_file
     from transformers import CLIPImageProcessor
     sd = synth.make_state_dict(g, seed=0)
-    model_dir = os.path.join(root, "vcoder_ds_llava-tiny")
-    tower = os.path.join(root, "tower")
+    model_dir = os.path.join(root, name)
+    tower = os.path.join(root, "tower_" + name)
     os.makedirs(model_dir)
     os.makedirs(tower)
     vt = "model.vision_tower.vision_tower."
@@ -277,3 +277,28 @@ def test_reference_chat_generate_stream_runs_unmodified(rig):
     params["temperature"] = 0.0
     list(c.generate_stream(params))
     assert eng.calls[-3][0] == "set_sampling" and eng.calls[-3][1] is False
+
+
+def test_reference_seg_eval_model_runs_unmodified_on_vcoder(rig):
+    """eval/model_seg_loader.py:99-166 with a VCoder (RGB + seg, non-DS) checkpoint: three tasks, each loading the model and
+    calling generate(images=, segs=, depths=None, do_sample=False, top_p=None, num_beams=1, max_new_tokens=512)."""
+    g = synth.PRESETS["tiny"].with_variant(synth.VARIANT_VCODER)
+    model_dir = _write_checkpoint(rig.tmp, g, name="vcoder_llava-tiny")
+    _jpg(os.path.join(rig.tmp, "rgb2", "0.jpg"), 40, 36, (10, 100, 200))
+    for task in ("semantic", "instance", "panoptic"):
+        _jpg(os.path.join(rig.tmp, "seg2", f"{task}_inference", "0.jpg"), 40, 36, (0, 90, 100))
+    out_prefix = os.path.join(rig.tmp, "answers_seg", "seg")
+    n0 = len(FakeEngine.instances)
+    rig.launch.main(["--reference", REFERENCE, "vcoder_llava.eval.model_seg_loader", "--model-path", model_dir,
+                     "--image-folder", os.path.join(rig.tmp, "rgb2"), "--use_seg", "--seg-image-folder", os.path.join(rig.tmp, "seg2"),
+                     "--output-file", out_prefix, "--temperature", "0"])
+    engines = FakeEngine.instances[n0:]
+    assert len(engines) == 3  # eval_model builds the model once per task
+    for task, eng in zip(("semantic", "instance", "panoptic"), engines):
+        assert eng.g.variant == synth.VARIANT_VCODER
+        text = open(f"{out_prefix}_{task}_1_0.txt").read()
+        assert f"<<ANSWER>>: {rig.tok.decode([11, 12, 13])}\n" in text
+        pre = [c for c in eng.calls if c[0] == "prefill"]
+        assert len(pre) == 1 and pre[0][2] and pre[0][3] and not pre[0][4]  # images + segs, no depths
+        assert [int(t) for t in pre[0][1][0] if t < 0] == [I, S]  # tokenizer_seg_token emits [IMAGE, SEG] (mm_utils.py:65-87)
+        assert ("set_sampling", False, 1.0, 50, 1.0) in eng.calls
