@@ -179,7 +179,7 @@ def run_reference(args):
     vals = []
     last = None
     for i in range(args.warmup + args.steps):
-        last = cpu_sample_tokens_per_s(args.batch, args.new_tokens, repeats=3)
+        last = cpu_sample_tokens_per_s(args.batch, args.new_tokens, repeats=5)
         if i >= args.warmup:
             vals.append(last["value"])
     v = sum(vals) / len(vals)
