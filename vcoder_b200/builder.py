@@ -3,7 +3,8 @@
 Same signature and the same 6-tuple `(tokenizer, model, image_processor, seg_image_processor, depth_image_processor,
 context_len)`; the model object is `vcoder_b200.model.VCoder{,DS}LlavaLlamaForCausalLM` (weights copied into
 libvcoder_b200.so) instead of an HF nn.Module.  Class dispatch by substring of `model_name` as in the reference
-(`builder.py:93-108`).  Quantised loading (`load_8bit` / `load_4bit`, bitsandbytes) is SURVEY §8 row f4 and raises.
+(`builder.py:93-108`).  `model_base` + `mm_projector.bin` (projector-only checkpoints, builder.py:82-92) loads the base LLM and the projector as
+plain LLaVA; LoRA checkpoints (peft) and quantised loading (`load_8bit` / `load_4bit`, bitsandbytes) raise.
 """
 from __future__ import annotations
 
@@ -53,9 +54,13 @@ def load_pretrained_model(model_path, model_base, model_name, load_8bit=False, l
                           device="cuda", tokenizer=None, max_batch: int = 8):
     if load_8bit or load_4bit:
         raise NotImplementedError("bitsandbytes 8/4-bit loading is SURVEY §8 row f4 (next); fp16 only")
-    if model_base is not None:
-        raise NotImplementedError("LoRA / delta checkpoints: merge offline with the reference's scripts/merge_lora_weights.py")
-    variant = variant_from_name(model_name)
+    if model_base is not None and "lora" in model_name.lower():
+        raise NotImplementedError("LoRA checkpoints (builder.py:44-81) need peft: merge offline with the reference's "
+                                  "scripts/merge_lora_weights.py and load the merged checkpoint")
+    if "llava" not in model_name.lower():
+        raise ValueError(f"{model_name}: not a LLaVA-family model (plain language models are not on the accelerated path)")
+    projector_only = model_base is not None  # builder.py:82-92: base LLM + mm_projector.bin, always LlavaLlamaForCausalLM
+    variant = synth.VARIANT_LLAVA if projector_only else variant_from_name(model_name)
     cfg = json.load(open(os.path.join(model_path, "config.json")))
     tower_path = cfg["mm_vision_tower"]
     vcfg_path = os.path.join(tower_path, "config.json")
@@ -65,9 +70,14 @@ def load_pretrained_model(model_path, model_base, model_name, load_8bit=False, l
 
     if tokenizer is None:
         from transformers import AutoTokenizer
-        tokenizer = AutoTokenizer.from_pretrained(model_path, use_fast=False)  # builder.py:92
+        tokenizer = AutoTokenizer.from_pretrained(model_base if projector_only else model_path, use_fast=False)  # builder.py:85/:96
 
-    sd = _read_state_dict(model_path)
+    if projector_only:
+        sd = _read_state_dict(model_base)
+        extra = torch.load(os.path.join(model_path, "mm_projector.bin"), map_location="cpu")  # builder.py:89-91
+        sd.update({k: v.to(torch.float16) for k, v in extra.items()})
+    else:
+        sd = _read_state_dict(model_path)
     # the CLIP tower is delay-loaded from its own checkpoint by the reference (builder.py:138-143)
     if not any(k.startswith(_VT) for k in sd):
         tower_sd = _read_state_dict(tower_path)
@@ -78,16 +88,17 @@ def load_pretrained_model(model_path, model_base, model_name, load_8bit=False, l
     try:
         from transformers import CLIPImageProcessor
         image_processor = CLIPImageProcessor.from_pretrained(tower_path)
-        # builder.py:146-151: same processor object for every modality the class has
-        seg_image_processor = image_processor if variant != synth.VARIANT_LLAVA else None
-        depth_image_processor = image_processor if variant == synth.VARIANT_VCODER_DS else None
+        # builder.py:138-151: the same processor object, handed out by SUBSTRING of the model name (not by class)
+        seg_image_processor = image_processor if "vcoder" in model_name.lower() else None
+        depth_image_processor = image_processor if "ds" in model_name.lower() else None
     except Exception:
         pass
 
     context_len = cfg.get("max_sequence_length", 2048)  # builder.py:133-136
     dev_index = torch.device(device).index or 0
-    model = build_model(model_name, g, sd, max_batch=max_batch, max_seq_len=max(context_len, 2048), device=dev_index,
-                        image_processor=image_processor)
+    from .model import LlavaLlamaForCausalLM
+    kw = dict(max_batch=max_batch, max_seq_len=max(context_len, 2048), device=dev_index, image_processor=image_processor)
+    model = LlavaLlamaForCausalLM(g, sd, **kw) if projector_only else build_model(model_name, g, sd, **kw)
     # generation defaults HF would read: generation_config.json, else the model config's eos/pad ids
     gen = {}
     gpath = os.path.join(model_path, "generation_config.json")
