@@ -140,6 +140,28 @@ int vcb_op_rmsnorm_f16(const vcb_half* x_dev, const vcb_half* w_dev, vcb_half* y
 int vcb_op_attention_vit_f16(const vcb_half* qkv_dev, int32_t B, int32_t S, int32_t heads, float scale,
                              vcb_half* out_dev, void* stream);
 
+/* LLaMA causal self-attention at prefill over the paged KV cache (transformers/models/llama/modeling_llama.py:199-222
+ * eager attention with the causal mask, reached from vcoder_ds_llava_llama.py:81): query row i of sequence b sits at position
+ * q_pos0 + i and attends to cached keys [0, q_pos0 + i].  q_dev [B*Tq, q_stride] fp16 (head h at columns h*128..), already
+ * rotated; k_pool_dev / v_pool_dev [n_pages][heads][64 tokens][128] fp16 already hold positions [0, q_pos0 + Tq);
+ * block_table_dev int32 [B][max_pages] = page id of tokens [64 p, 64 p + 64) of sequence b; out_dev [B*Tq, out_stride]. */
+int vcb_op_attention_prefill_f16(const vcb_half* q_dev, int64_t q_stride, const vcb_half* k_pool_dev,
+                                 const vcb_half* v_pool_dev, const int32_t* block_table_dev, int32_t max_pages, int32_t B,
+                                 int32_t heads, int32_t Tq, int32_t q_pos0, float scale, vcb_half* out_dev,
+                                 int64_t out_stride, void* stream);
+
+/* One decode step's attention over the paged KV cache: every cached position [0, ctx_len) is attended (the reference
+ * substitutes an all-ones mask, vcoder_ds_llava_arch.py:130-133).  qkv_dev [B, 3*heads*128] fp16 is the QKV row of the current
+ * token.  fuse_rope = 0: q is already rotated and the pools already hold position ctx_len - 1.  fuse_rope != 0 (what the
+ * engine's decode step runs): q and k are un-rotated; the kernel rotates them for position ctx_len - 1 (rotate-half,
+ * theta = rope_theta; modeling_llama.py:124-168) and appends the current k / v rows to the pools itself.  max_ctx >= ctx_len
+ * sizes the flash-decoding split grid exactly as a captured decode graph does (splits beyond ctx_len are empty).
+ * out_dev [B, heads*128]. */
+int vcb_op_attention_decode_f16(const vcb_half* qkv_dev, vcb_half* k_pool_dev, vcb_half* v_pool_dev,
+                                const int32_t* block_table_dev, int32_t max_pages, int32_t B, int32_t heads, int32_t ctx_len,
+                                int32_t max_ctx, int32_t fuse_rope, float rope_theta, float scale, vcb_half* out_dev,
+                                void* stream);
+
 /* HF GenerationMixin.sample() on a batch of fp16 logit rows [B,V] (V <= 32768): scores / temperature ->
  * TopKLogitsWarper(top_k; 0 = off; ties with the k-th score are kept) -> TopPLogitsWarper(top_p) -> softmax -> one draw per
  * row (transformers/generation/logits_process.py, generation/utils.py sample(); reached from serve/cli.py:121-132 with

@@ -342,8 +342,13 @@ def prefill_embeds(ids, sd, g, images, segs, depths):
     return splice_embeds(ids, sd, img_f, seg_f, dep_f, variant_ds, nz, g.variant, snz)
 
 
-def greedy_generate(ids, sd, g, images, segs, depths, max_new_tokens: int, return_logits: bool = False):
-    """-> new token ids [B, N] (int64) (+ per-step logits [N][B,V])."""
+def greedy_generate(ids, sd, g, images, segs, depths, max_new_tokens: int, return_logits: bool = False,
+                    forced_ids: Optional[torch.Tensor] = None):
+    """-> new token ids [B, N] (int64) (+ per-step logits [N][B,V]).
+
+    forced_ids [B, N] (test infrastructure, not reference behaviour): teacher forcing — the token FED BACK at step s is
+    forced_ids[:, s] instead of this function's own argmax (which is still what is returned), so the logits of a long
+    run stay comparable with an implementation whose near-tie choices legitimately differ."""
     x = prefill_embeds(ids, sd, g, images, segs, depths)
     cache = KVCache(g.llm_layers)
     emb = _f(sd["model.embed_tokens.weight"])
@@ -355,7 +360,8 @@ def greedy_generate(ids, sd, g, images, segs, depths, max_new_tokens: int, retur
         nxt = logits.argmax(dim=-1)
         out.append(nxt)
         if step + 1 < max_new_tokens:
-            logits = llama_forward(emb[nxt][:, None, :], sd, g, cache)
+            fed = nxt if forced_ids is None else forced_ids[:, step].to(torch.int64)
+            logits = llama_forward(emb[fed][:, None, :], sd, g, cache)
     ids_out = torch.stack(out, dim=1)
     return (ids_out, trace) if return_logits else ids_out
 

@@ -15,6 +15,7 @@ class RecordingEngine:
 
     def __init__(self, g, max_batch=8, max_seq_len=1536, device=0):
         self.g, self.bound, self.tdev = g, {}, torch.device("cpu")
+        self.max_batch, self.max_seq_len = max_batch, max_seq_len
         RecordingEngine.last = self
 
     def bind(self, sd):
@@ -36,7 +37,8 @@ def _configs(g, model_dir, tower):
     CLIPImageProcessor(size={"shortest_edge": g.vit_image_size}, crop_size=g.vit_image_size).save_pretrained(tower)
     json.dump({"hidden_size": g.llm_hidden, "intermediate_size": g.llm_ffn, "num_hidden_layers": g.llm_layers,
                "num_attention_heads": g.llm_heads, "vocab_size": g.llm_vocab, "rms_norm_eps": g.llm_rms_eps,
-               "mm_vision_tower": tower, "mm_vision_select_layer": -2, "eos_token_id": 2},
+               "mm_vision_tower": tower, "mm_vision_select_layer": -2, "eos_token_id": 2,
+               "max_position_embeddings": 4096, "image_aspect_ratio": "pad", "mm_use_im_start_end": False},
               open(os.path.join(model_dir, "config.json"), "w"))
 
 
@@ -59,6 +61,10 @@ def test_projector_only_checkpoint_with_model_base(tmp_path, monkeypatch):
     assert "model.mm_projector.0.weight" in eng.bound and "model.layers.0.self_attn.q_proj.weight" in eng.bound
     assert vt + "vision_model.embeddings.class_embedding" in eng.bound and "lm_head.weight" in eng.bound
     assert model.generation_config.eos_token_id == 2
+    # the engine is sized from max_position_embeddings (a DS prompt is ~1800 spliced tokens and the callers ask
+    # for 512 new ones), and every config.json key is visible on model.config (process_images reads image_aspect_ratio)
+    assert eng.max_seq_len == 4096 and model.config.max_position_embeddings == 4096
+    assert model.config.image_aspect_ratio == "pad" and model.config.mm_use_im_start_end is False
     # the processors follow SUBSTRINGS of the model name, not the class (builder.py:138-151)
     _, model, ip, sip, dip, _ = builder.load_pretrained_model(model_dir, base, "vcoder_ds_llava-projector", tokenizer="stub")
     assert type(model).__name__ == "LlavaLlamaForCausalLM" and sip is ip and dip is ip
@@ -75,3 +81,47 @@ def test_rejected_layouts(tmp_path, monkeypatch):
         builder.load_pretrained_model(str(tmp_path), str(tmp_path), "llava-tiny-lora", tokenizer="stub")
     with pytest.raises(ValueError):  # plain language models (builder.py:109-128) are not on the accelerated path
         builder.load_pretrained_model(str(tmp_path), None, "vicuna-7b", tokenizer="stub")
+
+
+def test_tower_hub_id_not_cached_is_a_clear_error(tmp_path, monkeypatch):
+    """Released checkpoints name the tower by hub id; offline and uncached that must be a FileNotFoundError that says
+    so, not a silent fall-back to default geometry."""
+    from vcoder_b200 import builder
+    monkeypatch.setenv("HF_HUB_OFFLINE", "1")
+    with pytest.raises(FileNotFoundError, match="neither a local directory nor in the local HF cache"):
+        builder.resolve_tower_path("openai/clip-vit-large-patch14-336-not-there")
+    assert builder.resolve_tower_path(str(tmp_path)) == str(tmp_path)
+
+
+def test_generate_clamps_to_the_kv_capacity_and_validates_pixels(monkeypatch):
+    """ADVICE r1: max_new_tokens is clamped to the engine capacity (HF ends at max_length, it does not raise up front);
+    stopping criteria combine with any(); wrong pixel shapes are refused before the pointers reach C."""
+    from vcoder_b200 import engine as eng_mod, model as model_mod
+
+    class Eng(RecordingEngine):
+        def set_sampling(self, *a, **k):
+            pass
+
+        def generate(self, ids, images, segs, depths, max_new_tokens):
+            self.asked = max_new_tokens
+            return torch.zeros(ids.shape[0], max_new_tokens, dtype=torch.int64)
+
+    monkeypatch.setattr("vcoder_b200.model.Engine", Eng)
+    g = synth.PRESETS["tiny"]
+    m = model_mod.VCoderDSLlavaLlamaForCausalLM(g, None, max_batch=2, max_seq_len=128)
+    ids = synth.make_prompt_ids(g, 2, seed=0, n_before=5, n_after=4)  # 13 ids, 3 specials -> at most 13 + 3*15 = 58 rows
+    out = m.generate(ids, images=None, max_new_tokens=512)
+    assert m._eng.asked == 128 - 58 and out.shape[1] == ids.shape[1] + 70
+    with pytest.raises(ValueError, match="engine holds"):
+        m.generate(torch.cat([ids] * 10, dim=1), images=None, max_new_tokens=4)
+    # pixel validation lives in the real Engine methods; exercise the checker without a device
+    e = object.__new__(eng_mod.Engine)
+    e.g, e.max_batch = g, 2
+    good = torch.zeros(2, 3, 56, 56)
+    e._check_pixels(good, "images", 2)
+    for bad in (torch.zeros(3, 3, 56, 56), torch.zeros(2, 3, 28, 28), torch.zeros(2, 1, 3, 56, 56)):
+        with pytest.raises(ValueError):
+            e._check_pixels(bad, "images", 2)
+    assert eng_mod._as_half_any([good[0], good[1]]).shape == (2, 3, 56, 56)
+    with pytest.raises(ValueError):
+        eng_mod._as_half_any([good[0], torch.zeros(3, 28, 28)])

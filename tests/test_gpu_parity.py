@@ -4,7 +4,7 @@ reference itself.  Integer work (splice plan, ids) is bit-exact; floating point 
 tolerances:
 
   single kernels (fp16 in/out, fp32 accumulate):  rel-RMS <= 5e-4, max-abs <= 2 fp16 ulps of the largest output
-  towers / projectors / logits (fp16 residual stream between kernels, N layers deep): rel-RMS <= 4e-3
+  towers / projectors / logits (fp16 residual stream between kernels, N layers deep): rel-RMS <= 2e-3
   greedy ids: equal to the oracle's wherever the oracle's top-1/top-2 logit margin exceeds 2x the measured logit
               error (near-ties below the fp16 noise floor are not decidable by ANY fp16 implementation).
 """
@@ -207,25 +207,25 @@ def test_tiny_against_reference_golden(variant, fname):
     if fname == "tiny_it_noseg.npz":
         segs[0] = 0  # is_seg_zero for row 0 (vcoder_it_llava_arch.py:148); row 1's seg map is encoded but not spliced
     tower = eng.tower_forward(images)
-    assert rel_rms(tower, torch.from_numpy(z["tower_features"])) <= 4e-3
-    assert rel_rms(eng.encode(0, images), torch.from_numpy(z["image_features"])) <= 4e-3
+    assert rel_rms(tower, torch.from_numpy(z["tower_features"])) <= 2e-3
+    assert rel_rms(eng.encode(0, images), torch.from_numpy(z["image_features"])) <= 2e-3
     if segs is not None:
-        assert rel_rms(eng.encode(1, segs), torch.from_numpy(z["seg_features"])) <= 4e-3
+        assert rel_rms(eng.encode(1, segs), torch.from_numpy(z["seg_features"])) <= 2e-3
     else:
         with pytest.raises(_lib.VcbError):
             eng.encode(1, images)
     if depths is not None:
-        assert rel_rms(eng.encode(2, depths), torch.from_numpy(z["depth_features"])) <= 4e-3  # via seg_mm_projector
+        assert rel_rms(eng.encode(2, depths), torch.from_numpy(z["depth_features"])) <= 2e-3  # via seg_mm_projector
     pre = eng.prefill(ids, images, segs, depths, want_logits=True, want_embeds=True)
     assert pre["spliced_len"] == z["inputs_embeds"].shape[1]
-    assert rel_rms(pre["embeds"], torch.from_numpy(z["inputs_embeds"])) <= 4e-3
+    assert rel_rms(pre["embeds"], torch.from_numpy(z["inputs_embeds"])) <= 2e-3
     n_new = z["greedy_ids"].shape[1]
     dec_ids, dec_logits = eng.decode(n_new - 1, want_logits=True)
     torch.cuda.synchronize()
     got_ids = torch.cat([pre["next_ids"][:, None], dec_ids], dim=1)
     got_logits = [pre["logits"]] + [dec_logits[s] for s in range(n_new - 1)]
     ref_logits = [torch.from_numpy(z["step_logits"][s]) for s in range(n_new)]
-    alive = check_greedy(got_ids, got_logits, torch.from_numpy(z["greedy_ids"]), ref_logits, logit_tol=3e-2)
+    alive = check_greedy(got_ids, got_logits, torch.from_numpy(z["greedy_ids"]), ref_logits, logit_tol=1e-2)
     assert bool(alive.any())
     # the CUDA-graph + host-buffer path (vcb_generate) must reproduce the eager path exactly
     gen = eng.generate(ids, images, segs, depths, max_new_tokens=n_new)
@@ -246,7 +246,7 @@ def test_tiny_quirks_on_device():
     pre = eng.prefill(ids2, images, segs, depths, want_logits=True, want_embeds=True)
     x_ref = orc.prefill_embeds(ids2, sd, g, images, segs, depths)
     assert pre["spliced_len"] == x_ref.shape[1] == 8 - 3 - 1 + 3 * g.n_patches
-    assert rel_rms(pre["embeds"], x_ref) <= 4e-3
+    assert rel_rms(pre["embeds"], x_ref) <= 2e-3
     # all-zero depth image + reachable <depth> token -> the reference's IndexError
     with pytest.raises(_lib.VcbError) as ei:
         eng.prefill(ids2, images, segs, torch.zeros_like(depths))
@@ -260,7 +260,7 @@ def test_tiny_quirks_on_device():
     pre = eng.prefill(t_ids, None, None, None, want_logits=True)
     emb = sd["model.embed_tokens.weight"].float()[t_ids]
     ref = orc.llama_forward(emb, sd, g, orc.KVCache(g.llm_layers))
-    assert max_abs(pre["logits"], ref) <= 3e-2
+    assert max_abs(pre["logits"], ref) <= 1e-2
 
 
 def test_decode_equals_prefill_property():
@@ -271,7 +271,7 @@ def test_decode_equals_prefill_property():
     _, lg = eng.decode(1, want_logits=True)
     ids_ext = torch.cat([ids, nxt[:, None]], dim=1)
     pre2 = eng.prefill(ids_ext, images, segs, depths, want_logits=True)
-    assert max_abs(lg[0], pre2["logits"]) <= 2e-2
+    assert max_abs(lg[0], pre2["logits"]) <= 1e-2
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -287,7 +287,7 @@ def test_vit_l_tower_real_size():
     got = eng.tower_forward(images)
     ref = orc.clip_tower_forward(images, sd, g)
     assert got.shape == (2, 576, 1024)
-    assert rel_rms(got, ref) <= 4e-3, rel_rms(got, ref)
+    assert rel_rms(got, ref) <= 2e-3, rel_rms(got, ref)
 
 
 @pytest.mark.parametrize("name,hidden,heads,ffn,layers,batch", [("7b", 4096, 32, 11008, 2, 8), ("13b", 5120, 40, 13824, 1, 4)])
@@ -308,8 +308,8 @@ def test_llama_real_width(name, hidden, heads, ffn, layers, batch):
     ref_ids, ref_logits = orc.greedy_generate(ids, sd, g, images, segs, depths, n_new, return_logits=True)
     got_ids = torch.cat([pre["next_ids"][:, None], dec_ids], dim=1)
     got_logits = [pre["logits"]] + [dec_logits[s] for s in range(n_new - 1)]
-    assert rel_rms(got_logits[0], ref_logits[0]) <= 4e-3, rel_rms(got_logits[0], ref_logits[0])  # prefill logits
-    alive = check_greedy(got_ids, got_logits, ref_ids, ref_logits, logit_tol=3e-2)  # teacher-forced while ids agree
+    assert rel_rms(got_logits[0], ref_logits[0]) <= 2e-3, rel_rms(got_logits[0], ref_logits[0])  # prefill logits
+    alive = check_greedy(got_ids, got_logits, ref_ids, ref_logits, logit_tol=1e-2)  # teacher-forced while ids agree
     assert bool(alive.any())
     gen = eng.generate(ids, images, segs, depths, max_new_tokens=n_new)  # CUDA-graph path
     assert torch.equal(gen, got_ids.cpu().long())

@@ -4,8 +4,8 @@ The reference has no such cache: serve/chat.py:41-159 and the serve/cli.py loop 
 whole conversation every turn.  So the checker for a cached turn is simply the full computation on the same inputs:
 the CPU oracle's greedy_generate on the turn's full prompt, and a FRESH engine's uncached vcb_prefill.
 
-  logits vs the oracle: max-abs <= 3e-2 (the engine-level fp16 tolerance of tests/test_gpu_parity.py)
-  logits vs an uncached prefill on the GPU: max-abs <= 2e-2 when previously GENERATED tokens are reused (their KV
+  logits vs the oracle: max-abs <= 1e-2 (the engine-level fp16 tolerance of tests/test_gpu_parity.py)
+  logits vs an uncached prefill on the GPU: max-abs <= 1e-2 when previously GENERATED tokens are reused (their KV
       entries came from the decode kernels, a different summation order), <= 2e-3 when only prompt positions are
       reused (position-wise the same arithmetic)
   reused_len / towers_skipped / ids: exact
@@ -75,14 +75,14 @@ def test_multi_turn_reuses_visual_and_generated_tokens():
     alive = torch.ones(B, dtype=torch.bool)
     for s in range(n2):
         err = (got_logits[s].float().cpu() - ref_logits[s]).abs().max(dim=-1).values
-        assert bool((err[alive] <= 3e-2).all()), (s, err.tolist())
+        assert bool((err[alive] <= 1e-2).all()), (s, err.tolist())
         top2 = ref_logits[s].topk(2, dim=-1).values
         same = got_ids[:, s] == ref_ids[:, s]
         assert not bool((alive & ~same & ((top2[:, 0] - top2[:, 1]) > 6e-2)).any()), (s, got_ids[:, s], ref_ids[:, s])
         alive &= same
     # vs an uncached prefill of the same prompt on a fresh handle
     ref2 = _fresh_logits(g, sd, ids2, px, B)
-    assert max_abs(pre2["logits"], ref2["logits"]) <= 2e-2
+    assert max_abs(pre2["logits"], ref2["logits"]) <= 1e-2
     # ---- turn 3 = "regenerate": the same prompt again -> everything but the last position is reused
     pre3 = eng.prefill(ids2, *px, want_logits=True, reuse=True)
     assert pre3["towers_skipped"] and pre3["reused_len"] == pre2["spliced_len"] - 1
@@ -115,7 +115,7 @@ def test_second_turn_against_the_reference_fixture():
         for s in range(n):
             rl = torch.from_numpy(ref_logits[s])
             err = (logits[s].float().cpu() - rl).abs().max(dim=-1).values
-            assert bool((err[alive] <= 3e-2).all()), (s, err.tolist())
+            assert bool((err[alive] <= 1e-2).all()), (s, err.tolist())
             top2 = rl.topk(2, dim=-1).values
             same = got[:, s] == torch.from_numpy(ref_ids[:, s])
             assert not bool((alive & ~same & ((top2[:, 0] - top2[:, 1]) > 6e-2)).any()), (s, got[:, s].tolist(), ref_ids[:, s].tolist())
@@ -220,7 +220,7 @@ def test_streaming_rollback_then_cached_turn():
     pre2 = eng.prefill(ids2, *px, want_logits=True, reuse=True)
     assert pre2["towers_skipped"] and pre2["reused_len"] == pre1["spliced_len"] + 3
     ref = _fresh_logits(g, sd, ids2, px, B)
-    assert max_abs(pre2["logits"], ref["logits"]) <= 2e-2
+    assert max_abs(pre2["logits"], ref["logits"]) <= 1e-2
 
 
 def test_shim_generate_uses_the_cache_for_interactive_calls():

@@ -37,6 +37,20 @@ def _read_state_dict(path: str) -> Dict[str, torch.Tensor]:
     return sd
 
 
+def resolve_tower_path(name: str) -> str:
+    """`mm_vision_tower` of the released checkpoints is the hub id `openai/clip-vit-large-patch14-336`, which the
+    reference resolves through `from_pretrained` (clip_encoder.py:22-27).  Accepts a local directory, else the local
+    HF cache (no network access is attempted)."""
+    if os.path.isdir(name):
+        return name
+    try:
+        from huggingface_hub import snapshot_download
+        return snapshot_download(name, local_files_only=True)
+    except Exception as e:
+        raise FileNotFoundError(f"vision tower '{name}' is neither a local directory nor in the local HF cache "
+                                f"(download it first, e.g. `huggingface-cli download {name}`)") from e
+
+
 def geometry_from_configs(cfg: dict, vcfg: dict, variant: int) -> ModelGeometry:
     """HF config.json keys the reference reads (vcoder_ds_llava_arch.py:34-49, CLIPVisionConfig, LlamaConfig)."""
     return ModelGeometry(
@@ -62,9 +76,8 @@ def load_pretrained_model(model_path, model_base, model_name, load_8bit=False, l
     projector_only = model_base is not None  # builder.py:82-92: base LLM + mm_projector.bin, always LlavaLlamaForCausalLM
     variant = synth.VARIANT_LLAVA if projector_only else variant_from_name(model_name)
     cfg = json.load(open(os.path.join(model_path, "config.json")))
-    tower_path = cfg["mm_vision_tower"]
-    vcfg_path = os.path.join(tower_path, "config.json")
-    vcfg = json.load(open(vcfg_path)) if os.path.exists(vcfg_path) else {}
+    tower_path = resolve_tower_path(cfg["mm_vision_tower"])
+    vcfg = json.load(open(os.path.join(tower_path, "config.json")))
     vcfg = vcfg.get("vision_config", vcfg)
     g = geometry_from_configs(cfg, vcfg, variant)
 
@@ -84,21 +97,26 @@ def load_pretrained_model(model_path, model_base, model_name, load_8bit=False, l
         for k, v in tower_sd.items():
             if k.startswith("vision_model."):
                 sd[_VT + k] = v
-    image_processor = seg_image_processor = depth_image_processor = None
-    try:
-        from transformers import CLIPImageProcessor
-        image_processor = CLIPImageProcessor.from_pretrained(tower_path)
-        # builder.py:138-151: the same processor object, handed out by SUBSTRING of the model name (not by class)
-        seg_image_processor = image_processor if "vcoder" in model_name.lower() else None
-        depth_image_processor = image_processor if "ds" in model_name.lower() else None
-    except Exception:
-        pass
+    # clip_encoder.py:24: a failure to load the processor surfaces here, as in the reference (callers dereference it)
+    from transformers import CLIPImageProcessor
+    image_processor = CLIPImageProcessor.from_pretrained(tower_path)
+    # builder.py:138-151: the same processor object, handed out by SUBSTRING of the model name (not by class)
+    seg_image_processor = image_processor if "vcoder" in model_name.lower() else None
+    depth_image_processor = image_processor if "ds" in model_name.lower() else None
 
     context_len = cfg.get("max_sequence_length", 2048)  # builder.py:133-136
+    # KV-cache capacity: the reference has no hard limit short of the rotary table (max_position_embeddings, 4096 for
+    # vicuna-1.5); a VCoder-DS prompt is ~1800 spliced tokens and the callers ask for max_new_tokens=512, so the
+    # `context_len` the reference merely reports (2048) must not cap the engine
+    max_seq_len = max(int(cfg.get("max_position_embeddings", 2048)), context_len, 2048)
     dev_index = torch.device(device).index or 0
     from .model import LlavaLlamaForCausalLM
-    kw = dict(max_batch=max_batch, max_seq_len=max(context_len, 2048), device=dev_index, image_processor=image_processor)
+    kw = dict(max_batch=max_batch, max_seq_len=max_seq_len, device=dev_index, image_processor=image_processor)
     model = LlavaLlamaForCausalLM(g, sd, **kw) if projector_only else build_model(model_name, g, sd, **kw)
+    # the callers hand `model.config` to process_images (eval/model_depth_loader.py:76, serve/chat.py:59): every
+    # config.json key (image_aspect_ratio = 'pad', mm_use_im_start_end, ...) must be visible on it
+    for k, v in cfg.items():
+        setattr(model.config, k, v)
     # generation defaults HF would read: generation_config.json, else the model config's eos/pad ids
     gen = {}
     gpath = os.path.join(model_path, "generation_config.json")

@@ -131,6 +131,64 @@ int vcb_op_attention_vit_f16(const vcb_half* qkv, int32_t B, int32_t S, int32_t 
   return attn_vit(a, ST(stream));
 }
 
+int vcb_op_attention_prefill_f16(const vcb_half* q, int64_t q_stride, const vcb_half* k_pool, const vcb_half* v_pool,
+                                 const int32_t* block_table, int32_t max_pages, int32_t B, int32_t heads, int32_t Tq,
+                                 int32_t q_pos0, float scale, vcb_half* out, int64_t out_stride, void* stream) {
+  VCB_TRY(require_device());
+  VCB_CHECK(q != nullptr && k_pool != nullptr && v_pool != nullptr && block_table != nullptr && out != nullptr, kErrInvalid,
+            "vcb_op_attention_prefill_f16: null argument");
+  VCB_CHECK(B >= 1 && heads >= 1 && Tq >= 1 && q_pos0 >= 0 && (q_pos0 + Tq + 63) / 64 <= max_pages, kErrInvalid,
+            "vcb_op_attention_prefill_f16: bad shape");
+  AttnPrefillParams a;
+  a.q = H(q); a.q_stride = q_stride;
+  a.k_pool = H(k_pool); a.v_pool = H(v_pool); a.block_table = block_table; a.max_pages = max_pages; a.page_tokens = 64;
+  a.out = H(out); a.out_stride = out_stride;
+  a.batch = B; a.n_heads = heads; a.seq_len = Tq; a.q_pos0 = q_pos0; a.head_dim = 128; a.scale = scale;
+  return attn_llama_prefill(a, ST(stream));
+}
+
+int vcb_op_attention_decode_f16(const vcb_half* qkv, vcb_half* k_pool, vcb_half* v_pool, const int32_t* block_table,
+                                int32_t max_pages, int32_t B, int32_t heads, int32_t ctx_len, int32_t max_ctx,
+                                int32_t fuse_rope, float rope_theta, float scale, vcb_half* out, void* stream) {
+  VCB_TRY(require_device());
+  VCB_CHECK(qkv != nullptr && k_pool != nullptr && v_pool != nullptr && block_table != nullptr && out != nullptr, kErrInvalid,
+            "vcb_op_attention_decode_f16: null argument");
+  VCB_CHECK(B >= 1 && heads >= 1 && ctx_len >= 1 && max_ctx >= ctx_len && (max_ctx + 63) / 64 <= max_pages, kErrInvalid,
+            "vcb_op_attention_decode_f16: bad shape");
+  cudaStream_t st = ST(stream);
+  const int splits = attn_decode_splits(max_ctx);
+  const size_t n_po = static_cast<size_t>(B) * heads * splits * 128 * 4, n_pml = static_cast<size_t>(B) * heads * splits * 2 * 4;
+  const size_t n_cs = fuse_rope ? static_cast<size_t>(ctx_len) * 64 * sizeof(float2) : 0;
+  char* scratch = nullptr;
+  VCB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), n_po + n_pml + n_cs + 256, st));
+  AttnDecodeParams a;
+  a.part_o = reinterpret_cast<float*>(scratch);
+  a.part_ml = reinterpret_cast<float*>(scratch + n_po);
+  int32_t* ctx_dev = reinterpret_cast<int32_t*>(scratch + n_po + n_pml);
+  std::vector<float2> tab;
+  int rc = kOk;
+  cudaError_t ce = cudaMemcpyAsync(ctx_dev, &ctx_len, 4, cudaMemcpyHostToDevice, st);
+  if (ce == cudaSuccess && fuse_rope) {
+    tab.resize(static_cast<size_t>(ctx_len) * 64);
+    build_rope_table(tab.data(), ctx_len, 128, rope_theta);
+    float2* cs_dev = reinterpret_cast<float2*>(scratch + n_po + n_pml + 256);
+    ce = cudaMemcpyAsync(cs_dev, tab.data(), n_cs, cudaMemcpyHostToDevice, st);
+    a.cos_sin = cs_dev; a.k_pool_w = H(k_pool); a.v_pool_w = H(v_pool);
+  }
+  if (ce == cudaSuccess) {
+    a.q = H(qkv); a.q_stride = 3L * heads * 128; a.k_pool = H(k_pool); a.v_pool = H(v_pool);
+    a.block_table = block_table; a.max_pages = max_pages; a.page_tokens = 64;
+    a.ctx_len = ctx_dev; a.max_ctx = max_ctx; a.out = H(out); a.batch = B; a.n_heads = heads; a.scale = scale;
+    rc = attn_llama_decode(a, st);
+  }
+  cudaFreeAsync(scratch, st);
+  const cudaError_t se = cudaStreamSynchronize(st);  // ctx_len / tab are host stack / heap buffers
+  VCB_CUDA(ce);
+  VCB_TRY(rc);
+  VCB_CUDA(se);
+  return kOk;
+}
+
 int vcb_splice_plan(int32_t variant, const int64_t* ids, int32_t B, int32_t T, int32_t n_patches, int32_t has_seg,
                     const uint8_t* depth_nonzero, int32_t* plan_out, int64_t plan_cap, int32_t* out_len) {
   VCB_CHECK(ids != nullptr && out_len != nullptr && B >= 1 && T >= 1, kErrInvalid, "vcb_splice_plan: bad arguments");

@@ -19,10 +19,17 @@ def _stream_ptr() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def _as_half_any(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
-    """fp16, contiguous, on whatever device it already lives (host buffers are copied by the library)."""
+def _as_half_any(t) -> Optional[torch.Tensor]:
+    """fp16, contiguous, on whatever device it already lives (host buffers are copied by the library).  A list of
+    [3,S,S] tensors (clip_encoder.py:40-45 accepts one) is stacked."""
     if t is None:
         return None
+    if isinstance(t, (list, tuple)):
+        if not t or any(not torch.is_tensor(x) or x.dim() != 3 or x.shape != t[0].shape for x in t):
+            raise ValueError("a list of images must hold [3,S,S] tensors of one shape (mixed sizes are not supported)")
+        t = torch.stack(list(t), dim=0)
+    if not torch.is_tensor(t):
+        raise ValueError(f"images must be a tensor or a list of tensors, not {type(t).__name__}")
     if t.dtype != torch.float16:
         t = t.to(torch.float16)
     return t.contiguous()
@@ -85,8 +92,21 @@ class Engine:
             del keep
 
     # ------------------------------------------------------------------------------------------------
+    def _check_pixels(self, t: Optional[torch.Tensor], what: str, batch: Optional[int] = None):
+        """The library copies n*3*S*S halves from the pointer it is given: anything else must be refused here."""
+        if t is None:
+            return
+        S = self.g.vit_image_size
+        if t.dim() != 4 or tuple(t.shape[1:]) != (3, S, S):
+            raise ValueError(f"{what}: expected [n, 3, {S}, {S}] (the tower's image size), got {tuple(t.shape)}")
+        if batch is not None and t.shape[0] != batch:
+            raise ValueError(f"{what}: {t.shape[0]} images for a batch of {batch} sequences")
+        if batch is None and not 1 <= t.shape[0] <= 3 * self.max_batch:
+            raise ValueError(f"{what}: {t.shape[0]} images, this handle takes 1..{3 * self.max_batch} per call")
+
     def tower_forward(self, pixels: torch.Tensor) -> torch.Tensor:
         px = _as_half_any(pixels)
+        self._check_pixels(px, "tower_forward")
         n = px.shape[0]
         out = torch.empty(n, self.g.n_patches, self.g.vit_hidden, dtype=torch.float16, device=self.tdev)
         with self.lock:
@@ -95,6 +115,7 @@ class Engine:
 
     def encode(self, modality: int, pixels: torch.Tensor) -> torch.Tensor:
         px = _as_half_any(pixels)
+        self._check_pixels(px, "encode")
         n = px.shape[0]
         out = torch.empty(n, self.g.n_patches, self.g.llm_hidden, dtype=torch.float16, device=self.tdev)
         with self.lock:
@@ -112,6 +133,8 @@ class Engine:
         B, T = ids_h.shape
         self._last_batch = B
         im, sg, dp = _as_half_any(images), _as_half_any(segs), _as_half_any(depths)
+        for t, what in ((im, "images"), (sg, "segs"), (dp, "depths")):
+            self._check_pixels(t, what, B)
         nxt = torch.empty(B, dtype=torch.int32, device=self.tdev)
         logits = torch.empty(B, self.g.llm_vocab, dtype=torch.float16, device=self.tdev) if want_logits else None
         n_vis = 3 * self.g.n_patches
@@ -150,6 +173,8 @@ class Engine:
         B, T = ids_h.shape
         self._last_batch = B
         im, sg, dp = _as_half_any(images), _as_half_any(segs), _as_half_any(depths)
+        for t, what in ((im, "images"), (sg, "segs"), (dp, "depths")):
+            self._check_pixels(t, what, B)
         out = torch.empty(B, max_new_tokens, dtype=torch.int64)
         with self.lock:
             _lib.check(self.lib.vcb_generate(self.h, _lib.ptr(ids_h), B, T, _lib.ptr(im), _lib.ptr(sg), _lib.ptr(dp),

@@ -187,6 +187,14 @@ class _VCoderBase:
             self._eng.set_sampling(False)
         dev = input_ids.device
         B = input_ids.shape[0]
+        # capacity: generation ends at the KV-cache capacity like HF's max_length ends it, instead of failing up front.
+        # Upper bound of the spliced length: every special token replaced by n_patches rows.
+        n_special = int((input_ids < 0).sum(dim=1).max()) if input_ids.numel() else 0
+        room = self._eng.max_seq_len - (input_ids.shape[1] + n_special * (self.geometry.n_patches - 1))
+        if room < 1:
+            raise ValueError(f"Input length of input_ids is {input_ids.shape[1]} ({n_special} special tokens x "
+                             f"{self.geometry.n_patches} patches), but the engine holds {self._eng.max_seq_len} positions")
+        max_new_tokens = min(int(max_new_tokens), room)
         interactive = streamer is not None or bool(stopping_criteria) or eos_token_id is not None
         try:
             if not interactive:
@@ -213,7 +221,7 @@ class _VCoderBase:
                 if eos is not None:
                     unfinished = unfinished & torch.tensor([int(t) not in eos for t in nxt.tolist()])
                     done = not bool(unfinished.any())
-                if stopping_criteria and all(bool(sc(seq, None)) for sc in stopping_criteria):
+                if stopping_criteria and any(bool(sc(seq, None)) for sc in stopping_criteria):  # StoppingCriteriaList.__call__
                     done = True
                 return done
 
