@@ -293,6 +293,27 @@ uint64_t vcb_launch_count(void);
 int vcb_profile_enable(int32_t on);
 int vcb_profile_read(float* ms_by_category, uint64_t* launches_by_category, int32_t n_categories);
 
+/* Hardware micro-benchmarks that size the attention kernels (tools/microbench.py; never called by the engine).
+ * which = 0: TMEM -> register read rate with `warps` warps per CTA and `param` tcgen05.ld.32x32b.x32 in flight per warp;
+ * *result = bytes per clock per SM.  which = 1: MUFU ex2.approx rate (param != 0: one FFMA between the ex2);
+ * *result = ex2 per clock per SM. */
+int vcb_microbench(int32_t which, int32_t warps, int32_t param, int32_t iters, float* result);
+
+/* Tuning hook (tools/bench_decode.py): pipeline shape of the weight-streaming kernel for GEMMs with this (N, K): `warps`
+ * per CTA (2, 4, 8; 0 = built-in choice) x `depth` stages of 8 KiB per warp (1..4; 0 = built-in choice).  Results do not
+ * depend on it bit for bit only when `warps` is unchanged (the split of K across warps fixes the summation order).
+ * Captured decode graphs keep the shape they were captured with. */
+int vcb_tune_skinny(int32_t N, int32_t K, int32_t warps, int32_t depth);
+
+/* Device-side timeline of the decode-step kernels (tools/trace_decode.py; evidence for DESIGN.md section 3.1).  Between
+ * vcb_trace_begin and vcb_trace_read every CTA of the weight-streaming GEMM, the decode attention kernels and the small
+ * RMSNorm launches stamps %globaltimer (ns) at entry, after its grid-dependency wait and at its end; works inside the
+ * captured decode graph (a replay overwrites the slots, so the LAST step is what is read).  launches_out [max_launches][4]
+ * = {kind (0 GEMM, 1 attention split, 2 attention combine, 3 rmsnorm), CTAs, first slot, aux (N / splits / H)};
+ * stamps_out [cap] uint64, three per CTA.  vcb_trace_read synchronises the device and closes the trace. */
+int vcb_trace_begin(int32_t max_ctas);
+int vcb_trace_read(int32_t* launches_out, int32_t max_launches, int32_t* n_launches, uint64_t* stamps_out, int64_t cap);
+
 /* The decode step's weight-streaming GEMMs alone (every layer's qkv, o, gate|up, down, then lm_head) on the bound
  * weights with batch B, back to back as inside the decode graph, `rounds` times between two CUDA events on the
  * launching stream (one untimed warm-up round first).  *ms_total = elapsed ms, *launches = kernels timed.  Invalidates

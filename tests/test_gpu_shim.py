@@ -24,6 +24,8 @@ def _write_checkpoint(tmp, g, sd):
     json.dump({"hidden_size": g.vit_hidden, "intermediate_size": g.vit_ffn, "num_hidden_layers": g.vit_layers,
                "num_attention_heads": g.vit_heads, "image_size": g.vit_image_size, "patch_size": g.vit_patch,
                "layer_norm_eps": g.vit_ln_eps}, open(os.path.join(tower, "config.json"), "w"))
+    from transformers import CLIPImageProcessor  # the tower directory of a real checkpoint carries its processor config
+    CLIPImageProcessor(size={"shortest_edge": g.vit_image_size}, crop_size=g.vit_image_size).save_pretrained(tower)
     save_file({k: v.contiguous() for k, v in sd.items() if not k.startswith(vt)}, os.path.join(tmp, "model.safetensors"))
     json.dump({"hidden_size": g.llm_hidden, "intermediate_size": g.llm_ffn, "num_hidden_layers": g.llm_layers,
                "num_attention_heads": g.llm_heads, "vocab_size": g.llm_vocab, "rms_norm_eps": g.llm_rms_eps,

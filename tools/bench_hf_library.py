@@ -83,8 +83,8 @@ def encode(tower, proj, which, pixels, select_layer=-2):
 
 
 @torch.no_grad()
-def generate(g, tower, llm, proj, ids, images, segs, depths, n_new):
-    """-> (new ids [B, n_new] on the host, per-step logits list or None)"""
+def generate(g, tower, llm, proj, ids, images, segs, depths, n_new, keep_trace=True):
+    """-> (new ids [B, n_new] on the host, per-step logits list or None).  keep_trace=False: no per-step host copy."""
     from vcoder_b200 import synth
     from vcoder_b200.engine import splice_plan
     B = ids.shape[0]
@@ -102,14 +102,51 @@ def generate(g, tower, llm, proj, ids, images, segs, depths, n_new):
     out = llm.model(inputs_embeds=x, use_cache=True)
     past = out.past_key_values
     logits = llm.lm_head(out.last_hidden_state[:, -1])
-    new, trace = [logits.argmax(-1)], [logits.float().cpu()]
+    new, trace = [logits.argmax(-1)], ([logits.float().cpu()] if keep_trace else None)
     for _ in range(n_new - 1):
         out = llm.model(input_ids=new[-1][:, None], past_key_values=past, use_cache=True)
         past = out.past_key_values
         logits = llm.lm_head(out.last_hidden_state[:, -1])
         new.append(logits.argmax(-1))
-        trace.append(logits.float().cpu())
+        if keep_trace:
+            trace.append(logits.float().cpu())
     return torch.stack(new, dim=1).cpu(), trace
+
+
+def measure(g, dev, B, N, reps=2, engine_ids=None, seed=0):
+    """bench.py's `library_baseline`: the job through the HF library modules in fp16 on `dev` (1 warm-up + `reps` timed
+    runs, wall clock with synchronize on both sides), and where its greedy ids first differ from `engine_ids` [B, N]."""
+    from vcoder_b200 import synth
+    tower, llm, proj = build_modules(g, str(dev), torch.float16, seed=seed)
+    ids = synth.make_prompt_ids(g, B, seed=0).to(dev)
+    px = [synth.make_pixels(g, B, s).to(dev, torch.float16) for s in (1, 2, 3)]
+    new, trace = generate(g, tower, llm, proj, ids, *px, N)  # warm-up; its logits serve the token comparison
+    times = []
+    for r in range(reps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        new2, _ = generate(g, tower, llm, proj, ids, *px, N, keep_trace=False)
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    times.sort()
+    t = times[len(times) // 2]
+    out = {"value": B * N / t, "unit": "tokens/s", "kind": "hf-fp16-eager", "ms_per_job": 1e3 * t, "reps": reps,
+           "transformers": __import__("transformers").__version__, "torch": torch.__version__,
+           "what": "transformers CLIPVisionModel + LlamaForCausalLM (eager attention, fp16, HF KV cache) with the reference's glue "
+                   "restated in torch (tools/bench_hf_library.py), same seeded weights, same GPU"}
+    if engine_ids is not None:
+        same = (engine_ids.cpu() == new)
+        first = [int((~same[b]).nonzero()[0]) if not bool(same[b].all()) else N for b in range(B)]
+        margins = []
+        for b in range(B):
+            if first[b] < N:
+                top2 = trace[first[b]][b].topk(2).values
+                margins.append(round(float(top2[0] - top2[1]), 5))
+        out["engine_tokens_equal_until"] = first
+        out["hf_top2_margin_at_first_divergence"] = margins
+    del tower, llm, proj
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():

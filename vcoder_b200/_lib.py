@@ -78,6 +78,10 @@ SIGNATURES = {
     "vcb_op_sample_f16": (C.c_int, [_p, _i32, _i32, _f, _i32, _f, C.c_uint64, _i32, _p, _p, _p]),
     "vcb_op_preprocess_u8": (C.c_int, [_p, _i32, _i32, _p, _i32, _p, _p, _p, _p]),
     "vcb_philox_uniform": (C.c_float, [C.c_uint64, C.c_uint32, C.c_uint32]),
+    "vcb_microbench": (C.c_int, [_i32, _i32, _i32, _i32, _p]),
+    "vcb_tune_skinny": (C.c_int, [_i32, _i32, _i32, _i32]),
+    "vcb_trace_begin": (C.c_int, [_i32]),
+    "vcb_trace_read": (C.c_int, [_p, _i32, _p, _p, _i64]),
     "vcb_bench_weight_stream": (C.c_int, [_p, _i32, _i32, _p, _p, _p]),
     "vcb_reset": (C.c_int, [_p]),
     "vcb_launch_count": (C.c_uint64, []),

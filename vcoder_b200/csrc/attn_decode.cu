@@ -8,6 +8,8 @@
 // one 128-dim row with 16-byte loads; per page each thread issues its 8 K-row and 8 V-row loads back to back (16
 // independent 16-byte loads in flight) and only then reduces.  Every half-warp runs its own online softmax, so the
 // main loop has no block-level synchronisation; the 8 partial (max, sum, acc) states are merged once through smem.
+#include <cstdlib>
+
 #include "common.h"
 #include "kernels.h"
 #include "ptx.cuh"
@@ -32,11 +34,18 @@ __device__ __forceinline__ uint4 ldg_stream16(const void* p) {
   return r;
 }
 
+// CLUSTER = true: the `splits` CTAs of one (sequence, head) form a thread-block cluster; the partial (max, sum, acc) states
+// stay in shared memory and CTA 0 of the cluster merges them through distributed shared memory and writes the fp16 output
+// itself — no partial buffers in HBM, no combine kernel (one launch and one dependency boundary less per layer).
+template <bool CLUSTER>
 __global__ void __launch_bounds__(kDecThreads)
 attn_decode_split_kernel(AttnDecodeParams p, int splits) {
   __shared__ float s_acc[8][kDH];
   __shared__ float s_m[8], s_l[8];
+  __shared__ float s_fin[kDH + 2];  // CLUSTER: this split's merged acc[128], max, sum (read by CTA 0 of the cluster)
   griddep_launch();
+  const int cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  trace_mark(p.trace, cta_lin, 0);
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x, hw = tid >> 4, l16 = tid & 15;
   const int k0 = split * kChunk;
@@ -55,10 +64,17 @@ attn_decode_split_kernel(AttnDecodeParams p, int splits) {
     }
   }
   griddep_wait();  // q and the current token's K/V row come from the kernels just before this one
+  trace_mark(p.trace, cta_lin, 1);
   const int ctx = *p.ctx_len;
   const long pidx = (static_cast<long>(b) * p.n_heads + h) * splits + split;
-  if (k0 >= ctx) {
-    if (tid == 0) { p.part_ml[pidx * 2] = -INFINITY; p.part_ml[pidx * 2 + 1] = 0.f; }
+  if (k0 >= ctx) {  // empty split of a graph sized for a longer context (never split 0: ctx >= 1)
+    if constexpr (CLUSTER) {
+      if (tid == 0) { s_fin[kDH] = -INFINITY; s_fin[kDH + 1] = 0.f; }
+      cluster_sync_all();  // publish
+      cluster_sync_all();  // CTA 0 has read
+    } else {
+      if (tid == 0) { p.part_ml[pidx * 2] = -INFINITY; p.part_ml[pidx * 2 + 1] = 0.f; }
+    }
     return;
   }
   const int nkeys = min(kChunk, ctx - k0);
@@ -186,14 +202,38 @@ attn_decode_split_kernel(AttnDecodeParams p, int splits) {
     o += wgt * s_acc[w][tid];
     L += wgt * s_l[w];
   }
-  p.part_o[pidx * kDH + tid] = o;
-  if (tid == 0) { p.part_ml[pidx * 2] = M; p.part_ml[pidx * 2 + 1] = L; }
+  if constexpr (CLUSTER) {
+    s_fin[tid] = o;
+    if (tid == 0) { s_fin[kDH] = M; s_fin[kDH + 1] = L; }
+    cluster_sync_all();
+    if (split == 0) {  // cluster rank == blockIdx.x: the cluster spans the whole x dimension
+      const uint32_t fin = smem_u32(s_fin);
+      float Mg = M;
+      for (int r = 1; r < splits; ++r) Mg = fmaxf(Mg, ld_dsmem_f32(dsmem_addr(fin + kDH * 4, r)));
+      float num = o * exp2f(M - Mg), den = L * exp2f(M - Mg);  // split 0 is never empty: M is finite
+      for (int r = 1; r < splits; ++r) {
+        const float mr = ld_dsmem_f32(dsmem_addr(fin + kDH * 4, r));
+        if (mr == -INFINITY) continue;
+        const float w = exp2f(mr - Mg);
+        num += w * ld_dsmem_f32(dsmem_addr(fin + tid * 4, r));
+        den += w * ld_dsmem_f32(dsmem_addr(fin + (kDH + 1) * 4, r));
+      }
+      p.out[static_cast<long>(b) * p.n_heads * kDH + h * kDH + tid] = __float2half_rn(num / den);
+    }
+    cluster_sync_all();  // the other CTAs' shared memory stays alive until CTA 0 has read it
+  } else {
+    p.part_o[pidx * kDH + tid] = o;
+    if (tid == 0) { p.part_ml[pidx * 2] = M; p.part_ml[pidx * 2 + 1] = L; }
+  }
+  trace_mark(p.trace, cta_lin, 2);
 }
 
 __global__ void __launch_bounds__(kDH)
 attn_decode_combine_kernel(AttnDecodeParams p, int splits) {
   griddep_launch();
+  trace_mark(p.trace2, blockIdx.x, 0);
   griddep_wait();
+  trace_mark(p.trace2, blockIdx.x, 1);
   const int bh = blockIdx.x;
   const int b = bh / p.n_heads, h = bh % p.n_heads;
   const int d = threadIdx.x;
@@ -209,6 +249,7 @@ attn_decode_combine_kernel(AttnDecodeParams p, int splits) {
     den += w * p.part_ml[pi * 2 + 1];
   }
   p.out[static_cast<long>(b) * p.n_heads * kDH + h * kDH + d] = __float2half_rn(num / den);
+  trace_mark(p.trace2, blockIdx.x, 2);
 }
 
 }  // namespace
@@ -224,8 +265,31 @@ int attn_llama_decode(const AttnDecodeParams& p_in, cudaStream_t stream) {
   VCB_CHECK(splits >= 1, kErrInvalid, "attn_llama_decode: empty context");
   VCB_CHECK(p.page_tokens == kPT, kErrInvalid, "attn_llama_decode: KV page must hold 64 tokens");
   dim3 grid(splits, p.n_heads, p.batch);
+  static int env_cl = -1;  // VCB_ATTN_DEC_CLUSTER=0: two kernels (split, combine through HBM partials)
+  if (env_cl < 0) { const char* e = getenv("VCB_ATTN_DEC_CLUSTER"); env_cl = e ? atoi(e) : 1; }
+  p.trace = trace_slots(kTraceAttnSplit, splits * p.n_heads * p.batch, splits);
+  if (env_cl != 0 && splits <= 8) {  // portable cluster size
+    KernelScope scope(kCatAttnDecode, stream, 1);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kDecThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    at[1].id = cudaLaunchAttributeClusterDimension;
+    at[1].val.clusterDim.x = static_cast<unsigned>(splits);
+    at[1].val.clusterDim.y = 1;
+    at[1].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 2;
+    VCB_CUDA(cudaLaunchKernelEx(&cfg, attn_decode_split_kernel<true>, p, splits));
+    return kOk;
+  }
+  p.trace2 = trace_slots(kTraceAttnCombine, p.batch * p.n_heads, splits);
   KernelScope scope(kCatAttnDecode, stream, 2);
-  VCB_CUDA(launch_pdl(attn_decode_split_kernel, grid, dim3(kDecThreads), 0, stream, p, splits));
+  VCB_CUDA(launch_pdl(attn_decode_split_kernel<false>, grid, dim3(kDecThreads), 0, stream, p, splits));
   VCB_CUDA(launch_pdl(attn_decode_combine_kernel, dim3(p.batch * p.n_heads), dim3(kDH), 0, stream, p, splits));
   return kOk;
 }

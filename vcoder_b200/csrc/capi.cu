@@ -383,6 +383,15 @@ int vcb_profile_enable(int32_t on) {
   return vcb::kOk;
 }
 
+int vcb_tune_skinny(int32_t N, int32_t K, int32_t warps, int32_t depth) { return vcb::tune_skinny(N, K, warps, depth); }
+
+int vcb_trace_begin(int32_t max_ctas) { return vcb::trace_begin(max_ctas); }
+
+int vcb_trace_read(int32_t* launches_out, int32_t max_launches, int32_t* n_launches, uint64_t* stamps_out, int64_t cap) {
+  VCB_CHECK(launches_out != nullptr && n_launches != nullptr && stamps_out != nullptr, vcb::kErrInvalid, "vcb_trace_read: null argument");
+  return vcb::trace_read(launches_out, max_launches, n_launches, reinterpret_cast<unsigned long long*>(stamps_out), cap);
+}
+
 int vcb_profile_read(float* ms_by_category, uint64_t* launches_by_category, int32_t n_categories) {
   VCB_CHECK(ms_by_category != nullptr && launches_by_category != nullptr && n_categories == vcb::kNumCat, vcb::kErrInvalid,
             "vcb_profile_read: need arrays of VCB_PROFILE_CATEGORIES entries");

@@ -104,6 +104,15 @@ struct KernelScope {  // RAII around one launcher call: counts kernels, optional
   ~KernelScope();
   int cat_; cudaStream_t st_; int rec_;
 };
+// Device-side timeline (tools/trace_decode.py): while a trace is open, launchers that support it hand every CTA three
+// 64-bit slots {enter, after griddepcontrol.wait, end} stamped with %globaltimer.  Works under graph capture (the slots are
+// baked into the captured parameters; a replay overwrites them), so the production decode graph can be inspected.
+enum TraceTag : int { kTraceSkinny = 0, kTraceAttnSplit = 1, kTraceAttnCombine = 2, kTraceRmsnorm = 3, kTraceOther = 4 };
+unsigned long long* trace_slots(int tag, int n_ctas, int aux);  // null when no trace is open
+int trace_begin(int max_ctas);
+int trace_epoch();  // changes whenever a trace is opened or closed (captured graphs hold the slot pointers)
+// launches_out: [max_launches][4] = {tag, n_ctas, base slot, aux}; stamps_out: [cap] u64 (3 per CTA).  Closes the trace.
+int trace_read(int32_t* launches_out, int max_launches, int32_t* n_launches, unsigned long long* stamps_out, long cap);
 uint64_t launch_count();
 void launch_count_add(int64_t n);
 void prof_enable(bool on);

@@ -116,9 +116,11 @@ layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ w, con
 constexpr int kRmsThreads = 128;
 constexpr int kRmsMaxChunks = 8;  // H <= 8192
 __global__ void __launch_bounds__(kRmsThreads)
-rmsnorm_kernel(const __half* __restrict__ x, const __half* __restrict__ w, __half* __restrict__ y, int H, float eps) {
+rmsnorm_kernel(const __half* __restrict__ x, const __half* __restrict__ w, __half* __restrict__ y, int H, float eps,
+               unsigned long long* trace) {
   __shared__ float scratch[kRmsThreads / 32];
   griddep_launch();
+  trace_mark(trace, blockIdx.x, 0);
   const long row = blockIdx.x;
   const int nch = H / 8;
   // the norm weight does not depend on the previous kernel: fetch it before the grid-dependency wait so that only ONE
@@ -130,6 +132,7 @@ rmsnorm_kernel(const __half* __restrict__ x, const __half* __restrict__ w, __hal
     wq[i] = (c < nch) ? __ldg(reinterpret_cast<const uint4*>(w) + c) : make_uint4(0, 0, 0, 0);
   }
   griddep_wait();
+  trace_mark(trace, blockIdx.x, 1);
   const uint4* xr = reinterpret_cast<const uint4*>(x + row * H);
   uint4 xq[kRmsMaxChunks];
 #pragma unroll
@@ -159,6 +162,7 @@ rmsnorm_kernel(const __half* __restrict__ x, const __half* __restrict__ w, __hal
       yr[c] = pack8(o);
     }
   }
+  trace_mark(trace, blockIdx.x, 2);
 }
 
 // ---- RoPE (rotate-half, theta 1e4, positions arange(past, past+T)) + append K/V to the paged cache
@@ -354,7 +358,8 @@ int layernorm_f16(const __half* x, const __half* w, const __half* b, __half* y, 
 int rmsnorm_f16(const __half* x, const __half* w, __half* y, long rows, int H, float eps, cudaStream_t s) {
   VCB_CHECK(H % 8 == 0 && H <= kRmsMaxChunks * kRmsThreads * 8, kErrInvalid, "rmsnorm_f16: H must be <= 8192, % 8");
   KernelScope scope(kCatNorm, s);
-  VCB_CUDA(launch_pdl(rmsnorm_kernel, dim3(static_cast<unsigned>(rows)), dim3(kRmsThreads), 0, s, x, w, y, H, eps));
+  unsigned long long* tr = rows <= 64 ? trace_slots(kTraceRmsnorm, static_cast<int>(rows), H) : nullptr;
+  VCB_CUDA(launch_pdl(rmsnorm_kernel, dim3(static_cast<unsigned>(rows)), dim3(kRmsThreads), 0, s, x, w, y, H, eps, tr));
   return kOk;
 }
 

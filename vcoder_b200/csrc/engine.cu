@@ -943,7 +943,9 @@ namespace {
 int ensure_graph(Engine* e, int max_ctx, cudaStream_t st, int* ran_eager) {
   const int B = e->batch, splits = attn_decode_splits(max_ctx), mode = e->sampling ? 1 : 0;
   *ran_eager = 0;
-  if (e->graph != nullptr && e->graph_batch == B && e->graph_splits == splits && e->graph_sampling == mode) return kOk;
+  if (e->graph != nullptr && e->graph_batch == B && e->graph_splits == splits && e->graph_sampling == mode &&
+      e->graph_trace_epoch == trace_epoch())
+    return kOk;
   VCB_TRY(decode_step_launch(e, max_ctx, st));
   *ran_eager = 1;
   if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
@@ -962,6 +964,7 @@ int ensure_graph(Engine* e, int max_ctx, cudaStream_t st, int* ran_eager) {
   e->graph_batch = B;
   e->graph_splits = splits;
   e->graph_sampling = mode;
+  e->graph_trace_epoch = trace_epoch();
   return kOk;
 }
 

@@ -80,7 +80,7 @@ struct Engine {
   cudaGraphExec_t graph = nullptr;
   cudaStream_t own_stream = nullptr;   // used when the caller hands us the legacy default stream
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
-  int graph_batch = 0, graph_splits = 0, graph_kernels = 0, graph_sampling = 0;
+  int graph_batch = 0, graph_splits = 0, graph_kernels = 0, graph_sampling = 0, graph_trace_epoch = 0;
   // f1: sampling + per-token streaming
   DevBuf sample_params;      // SampleDeviceParams (sample.cu), read by the sampling kernel inside the captured graph
   bool sampling = false;     // do_sample: the next-token kernel is sample_rows instead of argmax_rows

@@ -52,6 +52,8 @@ struct AttnDecodeParams {
   int batch = 0, n_heads = 0;
   int prefetch = 0;  // L2-prefetch the split's KV pages before the grid-dependency wait (VCB_ATTN_DEC_PF)
   float scale = 1.f;
+  unsigned long long* trace = nullptr;   // timeline slots of the split kernel (common.h trace_slots), else null
+  unsigned long long* trace2 = nullptr;  // ... of the combine kernel
 };
 int attn_llama_decode(const AttnDecodeParams& p, cudaStream_t stream);
 int attn_decode_splits(int max_ctx);
@@ -89,8 +91,10 @@ struct SkinnyParams {
   const float* cn_parts = nullptr;
   int cn_nparts = 0;
   float cn_eps = 0.f;
+  unsigned long long* trace = nullptr;  // timeline slots (common.h trace_slots), else null
 };
 int skinny_gemm(const SkinnyParams& p, cudaStream_t stream);
+int tune_skinny(int N, int K, int warps, int depth);  // ring shape of the TMA kernel for one (N, K); 0 = default
 int skinny_gemm_tma(const SkinnyParams& p, cudaStream_t stream);  // TMA / bulk-copy fed kernel (skinny_tma.cu); needs K % 64 == 0
 // W[N,K] row-major -> the streaming layout of the decode GEMM: [N/16][K/64][16 rows][128 B, 16-byte chunks pre-swizzled]
 int pack_skinny_weights(const __half* W, __half* Wp, int N, int K, cudaStream_t stream);

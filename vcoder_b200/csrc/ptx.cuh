@@ -38,6 +38,16 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// device-side timeline (common.h trace_slots): thread 0 of a CTA stamps slot `which` of its three
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace_mark(unsigned long long* tr, int cta, int which) {
+  if (tr != nullptr && threadIdx.x == 0) tr[static_cast<long>(cta) * 3 + which] = global_timer_ns();
+}
+
 // ---------------------------------------------------------------------------------------------
 // thread-block clusters: rank, barrier, distributed shared memory
 // ---------------------------------------------------------------------------------------------

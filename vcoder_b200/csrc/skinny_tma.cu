@@ -5,8 +5,10 @@
 // in flight per SM (up to ~190 KiB) no longer depend on registers or on L1 miss slots, which is what the plain-LDG
 // kernel runs out of.  Programmatic dependent launch: ring fill happens BEFORE the grid-dependency wait — weights do
 // not depend on the previous kernel, so HBM keeps streaming across kernel boundaries.
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "common.h"
 #include "kernels.h"
@@ -67,6 +69,7 @@ skinny_tma_kernel(const __grid_constant__ CUtensorMap tmW, SkinnyParams p) {
   BarT* bars = reinterpret_cast<BarT*>(smem + WARPS * kDepth * kStageBytes + sizeof(RedT) * WARPS + 8);
   float* s_ssq = reinterpret_cast<float*>(smem + WARPS * kDepth * kStageBytes + sizeof(RedT) * WARPS + 8 + sizeof(BarT) * WARPS);  // [WARPS][8*NB]
   griddep_launch();
+  trace_mark(p.trace, blockIdx.x, 0);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int row0 = blockIdx.x * 16;
@@ -116,6 +119,7 @@ skinny_tma_kernel(const __grid_constant__ CUtensorMap tmW, SkinnyParams p) {
   }
   __syncwarp();
   griddep_wait();  // X (and the residual) come from the previous kernel
+  trace_mark(p.trace, blockIdx.x, 1);
 
   const __half* xrow[NB];
   bool xok[NB];
@@ -303,6 +307,7 @@ skinny_tma_kernel(const __grid_constant__ CUtensorMap tmW, SkinnyParams p) {
       }
     }
   }
+  trace_mark(p.trace, blockIdx.x, 2);
 }
 
 template <int NB, int WARPS, int kDepth, int kGroup, bool PACKED = false, bool CHAIN = false>
@@ -350,10 +355,14 @@ int launch_tma_w(const CUtensorMap& tm, const SkinnyParams& p, int grid, int war
     if (depth == 3) return launch_tma<NB, 4, 3, 2>(tm, p, grid, stream);
     return launch_tma<NB, 4, 4, 2>(tm, p, grid, stream);
   }
-  if (warps >= 8) return launch_tma<NB, 8, 2, 4>(tm, p, grid, stream);
+  if (warps >= 8) {
+    if (depth <= 2) return launch_tma<NB, 8, 2, 4>(tm, p, grid, stream);
+    return launch_tma<NB, 8, 3, 4>(tm, p, grid, stream);
+  }
   if (warps >= 4) {
     if (depth <= 2) return launch_tma<NB, 4, 2, 4>(tm, p, grid, stream);
-    return launch_tma<NB, 4, 3, 4>(tm, p, grid, stream);
+    if (depth == 3) return launch_tma<NB, 4, 3, 4>(tm, p, grid, stream);
+    return launch_tma<NB, 4, 4, 4>(tm, p, grid, stream);
   }
   if (depth <= 2) return launch_tma<NB, 2, 2, 4>(tm, p, grid, stream);
   return launch_tma<NB, 2, 3, 4>(tm, p, grid, stream);
@@ -362,6 +371,40 @@ int launch_tma_w(const CUtensorMap& tm, const SkinnyParams& p, int grid, int war
 }  // namespace
 
 int make_tmap_w3d(CUtensorMap* m, const void* ptr, uint64_t K, uint64_t N, uint32_t box_kblocks);
+
+// Ring shape per GEMM shape.  The default (4 warps x 2 stages, three CTAs per SM) suits the shapes with many CTAs; the
+// N = hidden shapes (o-proj, down-proj: N/16 = 256 CTAs on 148 SMs) leave a third of the shared memory unused with it, so
+// they get deeper rings.  vcb_tune_skinny / VCB_SKINNY_TUNE="N:K:warps:depth,..." override the table (tools/bench_decode.py).
+namespace {
+struct SkinnyTune { int N, K, warps, depth; };
+std::vector<SkinnyTune>& tune_table() {
+  static std::vector<SkinnyTune> t;
+  static bool init = false;
+  if (!init) {
+    init = true;
+    if (const char* e = getenv("VCB_SKINNY_TUNE")) {
+      const char* q = e;
+      while (*q) {
+        SkinnyTune u{0, 0, 0, 0};
+        if (sscanf(q, "%d:%d:%d:%d", &u.N, &u.K, &u.warps, &u.depth) == 4) t.push_back(u);
+        while (*q && *q != ',') ++q;
+        if (*q == ',') ++q;
+      }
+    }
+  }
+  return t;
+}
+}  // namespace
+
+int tune_skinny(int N, int K, int warps, int depth) {
+  VCB_CHECK((warps == 0 || warps == 2 || warps == 4 || warps == 8) && depth >= 0 && depth <= 4, kErrInvalid,
+            "tune_skinny: warps in {0 (default), 2, 4, 8}, depth in 0..4");
+  auto& t = tune_table();
+  for (auto& u : t)
+    if (u.N == N && u.K == K) { u.warps = warps; u.depth = depth; return kOk; }
+  t.push_back({N, K, warps, depth});
+  return kOk;
+}
 
 int pack_skinny_weights(const __half* W, __half* Wp, int N, int K, cudaStream_t stream) {
   VCB_CHECK(W != nullptr && Wp != nullptr && N % 16 == 0 && K % 64 == 0, kErrInvalid,
@@ -391,6 +434,7 @@ int skinny_gemm_tma(const SkinnyParams& p_in, cudaStream_t stream) {
     VCB_CHECK((reinterpret_cast<uintptr_t>(p.Wp) & 15) == 0, kErrInvalid, "skinny_gemm: packed weights must be 16-byte aligned");
     static int env_pd = -1;
     if (env_pd < 0) { const char* e = getenv("VCB_SKINNY_TMA_DEPTH"); env_pd = e ? atoi(e) : 0; }
+    p.trace = trace_slots(kTraceSkinny, grid, p.N);
     KernelScope scope(kCatSkinny, stream);
     switch (nb) {
       case 1: return launch_packed<1>(p, grid, env_pd, stream);
@@ -408,9 +452,15 @@ int skinny_gemm_tma(const SkinnyParams& p_in, cudaStream_t stream) {
   if (env_d < 0) { const char* e = getenv("VCB_SKINNY_TMA_DEPTH"); env_d = e ? atoi(e) : 0; }
   if (env_w == 2 || env_w == 4 || env_w == 8) warps = env_w;
   if (env_d > 0) depth = env_d;
+  for (const auto& u : tune_table())
+    if (u.N == p.N && u.K == p.K) {
+      if (u.warps > 0) warps = u.warps;
+      if (u.depth > 0) depth = u.depth;
+    }
   if (p.pn_parts != nullptr || p.cn_parts != nullptr) group = 4;
   CUtensorMap tm;
   VCB_TRY(make_tmap_w3d(&tm, p.W, p.K, p.N, group));
+  p.trace = trace_slots(kTraceSkinny, grid, p.N);
   KernelScope scope(kCatSkinny, stream);
   switch (nb) {
     case 1: return launch_tma_w<1>(tm, p, grid, warps, depth, group, stream);
