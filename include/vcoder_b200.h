@@ -209,7 +209,8 @@ int vcb_destroy(vcb_handle h);
 int vcb_bind_weights(vcb_handle h, const vcb_tensor* tensors, int32_t n);
 
 /* CLIPVisionTower.forward (clip_encoder.py:39-51): pixels_any [n,3,S,S] fp16 -> out_any [n,P,D] fp16
- * = hidden_states[select_layer][:, 1:]. n <= 3*max_batch. */
+ * = hidden_states[select_layer][:, 1:].  Any n >= 1: batches beyond the handle's vision workspace (3*max_batch images)
+ * run in chunks of that size. */
 int vcb_tower_forward(vcb_handle h, const vcb_half* pixels_any, int32_t n, vcb_half* out_any, void* stream);
 
 /* encode_images (modality 0: mm_projector), encode_seg_images (1) / encode_depth_images (2): both seg_mm_projector

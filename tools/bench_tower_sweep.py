@@ -1,11 +1,12 @@
 """BASELINE.json configs[4]: ViT-L/14@336 three-tower throughput sweep (RGB + seg + depth through the ONE shared tower,
 SURVEY F1) — images/s, tower TFLOP/s and the attention kernel's share / HBM-yardstick fraction per batch size.
 
-    python tools/bench_tower_sweep.py [--batches 1,2,4,8,16,32] [--reps 5]        (1 GPU)
+    python tools/bench_tower_sweep.py [--batches 1,2,4,8,16,32,64,128,256] [--reps 5]        (1 GPU)
     python -m torch.distributed.run --nproc-per-node N ... tools/bench_tower_sweep.py   (N replicas, no collective on the
         data path: the per-rank rates are summed, times are max over ranks)
 
-`batch` = samples; every sample brings 3 images, so one tower call sees 3*batch images (the handle takes <= 96).
+`batch` = samples per GPU; every sample brings 3 images, so one vcb_tower_forward call sees 3*batch images (the handle's
+vision workspace holds 96; larger calls run in chunks of 96 inside the library).
 Pixels are resident in HBM; weights (582 MB) + activations of >= 3 images exceed nothing in particular, so the L2 is
 flushed between timed calls by writing a 256 MB buffer.  Prints one JSON line per batch size and a final summary line.
 """
@@ -23,7 +24,7 @@ import torch  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--batches", default="1,2,4,8,16,32")
+    ap.add_argument("--batches", default="1,2,4,8,16,32,64,128,256")
     ap.add_argument("--reps", type=int, default=5)
     args = ap.parse_args()
     from vcoder_b200 import _lib, synth
@@ -41,7 +42,7 @@ def main():
     lib = _lib.load()
     g = synth.PRESETS["vit_l"]
     batches = [int(b) for b in args.batches.split(",")]
-    eng = Engine(g, max_batch=max(batches), max_seq_len=64, device=local)
+    eng = Engine(g, max_batch=min(32, max(batches)), max_seq_len=64, device=local)
     eng.bind({k: v.to(dev) for k, v in synth.make_state_dict(g, seed=0, only_prefix="model.vision_tower.").items()})
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)

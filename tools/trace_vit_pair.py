@@ -1,0 +1,25 @@
+"""clock64 phase trace of CTA (0,0,0) of the pair-schedule ViT attention kernel (both softmax warpgroups), production shape."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+dbg = torch.zeros(256, dtype=torch.int64, device="cuda")
+os.environ["VCB_VIT_TRACE"] = hex(dbg.data_ptr())
+os.environ["VCB_VIT_ATTN"] = "pair"
+from vcoder_b200 import _lib
+lib = _lib.load()
+B, S, heads = 24, 577, 16
+D = heads * 64
+qkv = torch.randn(B * S, 3 * D, device="cuda").half()
+o = torch.empty(B * S, D, device="cuda", dtype=torch.float16)
+for _ in range(3):
+    lib.vcb_op_attention_vit_f16(_lib.ptr(qkv), B, S, heads, 0.125, _lib.ptr(o), None)
+torch.cuda.synchronize()
+d = dbg.cpu()
+t0 = int(d[128])
+print("cta cycles", int(d[129]) - t0)
+names = ["blk_start", "S_ready", "S_loaded", "max_done", "PVprev_done", "rescaled", "exp_P_done", "P_arrived"]
+for t in range(2):
+    print("tile", "AB"[t], " ".join(f"{n:>12s}" for n in names))
+    for j in range(5):
+        print("   ", j, " ".join(f"{int(d[(t * 8 + j) * 8 + k]) - t0:12d}" for k in range(8)))

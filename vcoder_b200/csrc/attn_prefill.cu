@@ -287,6 +287,13 @@ int attn_vit(const AttnPrefillParams& p, cudaStream_t stream) {
 int attn_llama_prefill(const AttnPrefillParams& p, cudaStream_t stream) {
   VCB_CHECK(p.head_dim == 128, kErrInvalid, "attn_llama_prefill: head_dim must be 128");
   VCB_CHECK(p.page_tokens == kBN, kErrInvalid, "attn_llama_prefill: KV page must hold 64 tokens");
+  // VCB_PREFILL_ATTN=legacy: the mma.sync / cp.async kernel of this file (A/B, and the fallback for unaligned buffers);
+  // read on every call so that one test process can compare the two
+  const char* e = getenv("VCB_PREFILL_ATTN");
+  const bool legacy = e != nullptr && std::string(e) == "legacy";
+  const bool aligned = p.q_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(p.q) & 15) == 0 && p.out_stride % 8 == 0 &&
+                       (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
+  if (!legacy && aligned) return attn_llama_prefill_tc5(p, stream);
   return launch_attn<128, true, true>(p, stream);
 }
 

@@ -38,6 +38,7 @@ struct VitPairParams {
   int S, D, n_heads;
   float scale_log2;
   uint32_t v_desc_hi, v_lbo;
+  long long* dbg;  // optional clock64 trace of CTA (0,0,0) (tools/trace_vit_pair.py; VCB_VIT_TRACE=<device address>)
 };
 
 // barriers: per tile t: S ready, S free, P ready[2 bufs], O done
@@ -62,6 +63,7 @@ attn_vit_pair_kernel(const __grid_constant__ CUtensorMap tm, VitPairParams p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pair = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) p.dbg[128] = clock64();
   const int S = p.S;
   const int nb = (S + kKB - 1) / kKB;
   const int row_base = b * S;
@@ -163,10 +165,14 @@ attn_vit_pair_kernel(const __grid_constant__ CUtensorMap tm, VitPairParams p) {
       const uint32_t o_addr = tmem + lane_off + kColO + t * kDh;
       float Mref = -INFINITY, L = 0.f;
 
+      const bool tr = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && q == 0 && lane == 0;
+#define VCB_STAMP(k) do { if (tr) p.dbg[(t * 8 + j) * 8 + (k)] = clock64(); } while (0)
       for (int j = 0; j < nb; ++j) {
         const int nk = min(kKB, S - j * kKB);
+        VCB_STAMP(0);
         mbar_wait(bar(kBarS + t), j & 1);
         tc_fence_after();
+        VCB_STAMP(1);
         uint32_t v[4][32];
         tmem_ld_32x32(s_addr, v[0]);
         tmem_ld_32x32(s_addr + 32, v[1]);
@@ -176,6 +182,7 @@ attn_vit_pair_kernel(const __grid_constant__ CUtensorMap tm, VitPairParams p) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(kBarSFree + t));
+        VCB_STAMP(2);
 
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
         if (nk == kKB) {
@@ -210,10 +217,12 @@ attn_vit_pair_kernel(const __grid_constant__ CUtensorMap tm, VitPairParams p) {
         }
         // P_{j-1} V_{j-1} must be complete before O is rescaled or the P tile is overwritten (it was issued right after
         // this warpgroup's previous arrival, so in steady state this wait is already satisfied)
+        VCB_STAMP(3);
         if (j > 0) {
           mbar_wait(bar(kBarO + t), (j - 1) & 1);
           tc_fence_after();
         }
+        VCB_STAMP(4);
         if (j > 0 && __any_sync(0xffffffffu, f != 1.f)) {
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
@@ -226,6 +235,7 @@ attn_vit_pair_kernel(const __grid_constant__ CUtensorMap tm, VitPairParams p) {
           }
           tmem_st_wait();
         }
+        VCB_STAMP(5);
         const float msc = Mref * sc;
         uint8_t* prow = smem + kOffP + t * 2 * kTile + r * 128;
         float l0 = 0.f, l1 = 0.f;
@@ -262,11 +272,14 @@ attn_vit_pair_kernel(const __grid_constant__ CUtensorMap tm, VitPairParams p) {
           }
         }
         L += l0 + l1;
+        VCB_STAMP(6);
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(kBarP + t));
+        VCB_STAMP(7);
       }
+#undef VCB_STAMP
 
       // ---- epilogue: O (TMEM) / l -> fp16
       mbar_wait(bar(kBarO + t), (nb - 1) & 1);
@@ -295,6 +308,7 @@ attn_vit_pair_kernel(const __grid_constant__ CUtensorMap tm, VitPairParams p) {
 
   tc_fence_before();
   __syncthreads();
+  if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) p.dbg[129] = clock64();
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
@@ -324,6 +338,8 @@ int attn_vit_pair(const AttnPrefillParams& a, cudaStream_t stream) {
   p.scale_log2 = a.scale * 1.4426950408889634f;
   p.v_desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);  // MN-major V: SBO 1024 B, version 1, SWIZZLE_128B
   p.v_lbo = 0;
+  p.dbg = nullptr;
+  if (const char* e = getenv("VCB_VIT_TRACE")) p.dbg = reinterpret_cast<long long*>(strtoull(e, nullptr, 16));
   const int q_tiles = (a.seq_len + kQ - 1) / kQ;
   dim3 grid((q_tiles + 1) / 2, a.n_heads, a.batch);
   KernelScope scope(kCatAttnVit, stream);

@@ -53,6 +53,7 @@ int vcb_op_gemm_f16(const vcb_half* A, int32_t lda, const vcb_half* W, int32_t l
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------------------------
+#include <algorithm>
 #include <vector>
 
 #include "engine.h"
@@ -159,8 +160,10 @@ int vcb_op_attention_decode_f16(const vcb_half* qkv, vcb_half* k_pool, vcb_half*
   const int splits = attn_decode_splits(max_ctx);
   const size_t n_po = static_cast<size_t>(B) * heads * splits * 128 * 4, n_pml = static_cast<size_t>(B) * heads * splits * 2 * 4;
   const size_t n_cs = fuse_rope ? static_cast<size_t>(ctx_len) * 64 * sizeof(float2) : 0;
+  const size_t n_sync = (static_cast<size_t>(B) * heads * 4 + 255) & ~static_cast<size_t>(255);
   char* scratch = nullptr;
-  VCB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), n_po + n_pml + n_cs + 256, st));
+  VCB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), n_po + n_pml + n_cs + 256 + n_sync, st));
+  cudaMemsetAsync(scratch + n_po + n_pml + 256 + n_cs, 0, n_sync, st);
   AttnDecodeParams a;
   a.part_o = reinterpret_cast<float*>(scratch);
   a.part_ml = reinterpret_cast<float*>(scratch + n_po);
@@ -178,6 +181,7 @@ int vcb_op_attention_decode_f16(const vcb_half* qkv, vcb_half* k_pool, vcb_half*
   if (ce == cudaSuccess) {
     a.q = H(qkv); a.q_stride = 3L * heads * 128; a.k_pool = H(k_pool); a.v_pool = H(v_pool);
     a.block_table = block_table; a.max_pages = max_pages; a.page_tokens = 64;
+    a.sync_counters = reinterpret_cast<int32_t*>(scratch + n_po + n_pml + 256 + n_cs);
     a.ctx_len = ctx_dev; a.max_ctx = max_ctx; a.out = H(out); a.batch = B; a.n_heads = heads; a.scale = scale;
     rc = attn_llama_decode(a, st);
   }
@@ -231,15 +235,22 @@ int vcb_tower_forward(vcb_handle h, const vcb_half* pixels, int32_t n, vcb_half*
   Engine* e = h->e;
   VCB_CUDA(cudaSetDevice(e->device));
   VCB_TRY(engine_check_bound(e, true, false));
-  VCB_CHECK(n >= 1 && n <= e->vit_max_images, kErrInvalid, "vcb_tower_forward: n must be in [1, 3*max_batch]");
+  VCB_CHECK(n >= 1, kErrInvalid, "vcb_tower_forward: n must be >= 1");
   const size_t img = 3ul * e->cfg.vit_image_size * e->cfg.vit_image_size * 2;
+  const size_t orow = static_cast<size_t>(e->P) * e->cfg.vit_hidden * 2;
   StreamGuard sg(e, ST(stream));
   e->feat_key = 0;  // pix / vh are overwritten: the prefix cache must not skip the towers on the next prefill
-  VCB_TRY(copy_any(e->pix.p, pixels, n * img, sg.st));
-  VCB_TRY(engine_tower(e, e->pix.as<__half>(), n, sg.st));
-  // feature_select 'patch': drop CLS; compact into vn then copy out (out may be host memory)
-  VCB_TRY(compact_patches(e->vh.as<__half>(), e->vn.as<__half>(), n, e->S, e->cfg.vit_hidden, sg.st));
-  return copy_any(out, e->vn.p, static_cast<size_t>(n) * e->P * e->cfg.vit_hidden * 2, sg.st);
+  // any number of images: the handle's vision workspaces hold 3*max_batch of them, larger batches run in chunks of that
+  // size (BASELINE configs[4] sweeps the tower to 256 images per call)
+  for (int i0 = 0; i0 < n; i0 += e->vit_max_images) {
+    const int m = std::min(e->vit_max_images, n - i0);
+    VCB_TRY(copy_any(e->pix.p, reinterpret_cast<const char*>(pixels) + i0 * img, m * img, sg.st));
+    VCB_TRY(engine_tower(e, e->pix.as<__half>(), m, sg.st));
+    // feature_select 'patch': drop CLS; compact into vn then copy out (out may be host memory)
+    VCB_TRY(compact_patches(e->vh.as<__half>(), e->vn.as<__half>(), m, e->S, e->cfg.vit_hidden, sg.st));
+    VCB_TRY(copy_any(reinterpret_cast<char*>(out) + i0 * orow, e->vn.p, m * orow, sg.st));
+  }
+  return kOk;
 }
 
 int vcb_encode(vcb_handle h, int32_t modality, const vcb_half* pixels, int32_t n, vcb_half* out, void* stream) {
@@ -251,15 +262,20 @@ int vcb_encode(vcb_handle h, int32_t modality, const vcb_half* pixels, int32_t n
             "vcb_encode: encode_depth_images exists on VCoder-DS only");
   VCB_CUDA(cudaSetDevice(e->device));
   VCB_TRY(engine_check_bound(e, true, true));
-  VCB_CHECK(n >= 1 && n <= e->vit_max_images, kErrInvalid, "vcb_encode: n must be in [1, 3*max_batch]");
+  VCB_CHECK(n >= 1, kErrInvalid, "vcb_encode: n must be >= 1");
   const size_t img = 3ul * e->cfg.vit_image_size * e->cfg.vit_image_size * 2;
+  const size_t orow = static_cast<size_t>(e->P) * e->cfg.llm_hidden * 2;
   StreamGuard sg(e, ST(stream));
   e->feat_key = 0;  // pix / vh / feats are overwritten
-  VCB_TRY(copy_any(e->pix.p, pixels, n * img, sg.st));
-  VCB_TRY(engine_tower(e, e->pix.as<__half>(), n, sg.st));
-  VCB_TRY(engine_project(e, 0, n * e->S, modality == 0 ? e->mm : e->seg, sg.st));
-  VCB_TRY(compact_patches(e->feats.as<__half>(), e->pmid.as<__half>(), n, e->S, e->cfg.llm_hidden, sg.st));
-  return copy_any(out, e->pmid.p, static_cast<size_t>(n) * e->P * e->cfg.llm_hidden * 2, sg.st);
+  for (int i0 = 0; i0 < n; i0 += e->vit_max_images) {  // chunks of the workspace capacity, as vcb_tower_forward
+    const int m = std::min(e->vit_max_images, n - i0);
+    VCB_TRY(copy_any(e->pix.p, reinterpret_cast<const char*>(pixels) + i0 * img, m * img, sg.st));
+    VCB_TRY(engine_tower(e, e->pix.as<__half>(), m, sg.st));
+    VCB_TRY(engine_project(e, 0, m * e->S, modality == 0 ? e->mm : e->seg, sg.st));
+    VCB_TRY(compact_patches(e->feats.as<__half>(), e->pmid.as<__half>(), m, e->S, e->cfg.llm_hidden, sg.st));
+    VCB_TRY(copy_any(reinterpret_cast<char*>(out) + i0 * orow, e->pmid.p, m * orow, sg.st));
+  }
+  return kOk;
 }
 
 int vcb_prefill(vcb_handle h, const int64_t* ids, int32_t B, int32_t T, const vcb_half* images, const vcb_half* segs,

@@ -256,7 +256,8 @@ constexpr int kArgThreads = 256;
 // embedding gather of the decode step + the producer half of layer 0's input RMSNorm (see SkinnyParams::pn_*)
 __global__ void __launch_bounds__(128)
 embed_gather_norm_kernel(const int32_t* __restrict__ ids, const __half* __restrict__ embed, __half* __restrict__ out,
-                         const __half* __restrict__ norm_w, __half* __restrict__ xn_out, float* __restrict__ parts, int H) {
+                         const __half* __restrict__ norm_w, __half* __restrict__ xn_out, float* __restrict__ rstd, float eps,
+                         int H) {
   __shared__ float scratch[4];
   griddep_launch();
   griddep_wait();
@@ -277,7 +278,7 @@ embed_gather_norm_kernel(const int32_t* __restrict__ ids, const __half* __restri
     on[c] = pack8(y);
   }
   const float tot = block_sum<128>(sq, scratch);
-  if (threadIdx.x == 0) parts[b] = tot;
+  if (threadIdx.x == 0) rstd[b] = rsqrtf(tot / static_cast<float>(H) + eps);
 }
 
 __global__ void __launch_bounds__(kArgThreads)
@@ -389,9 +390,9 @@ int embed_gather(const int32_t* ids, const __half* embed, __half* out, int B, in
 }
 
 int embed_gather_norm(const int32_t* ids, const __half* embed, __half* out, const __half* norm_w, __half* xn_out,
-                      float* parts, int B, int H, cudaStream_t s) {
+                      float* rstd, float eps, int B, int H, cudaStream_t s) {
   KernelScope scope(kCatMisc, s);
-  VCB_CUDA(launch_pdl(embed_gather_norm_kernel, dim3(B), dim3(128), 0, s, ids, embed, out, norm_w, xn_out, parts, H));
+  VCB_CUDA(launch_pdl(embed_gather_norm_kernel, dim3(B), dim3(128), 0, s, ids, embed, out, norm_w, xn_out, rstd, eps, H));
   return kOk;
 }
 

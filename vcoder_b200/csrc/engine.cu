@@ -174,6 +174,8 @@ int engine_create(const vcb_config* c, int device, Engine** out) {
   if (rc == kOk) rc = dev_alloc(e, &e->trace, B * c->max_seq_len * 4);
   if (rc == kOk) rc = dev_alloc(e, &e->part_o, B * c->llm_heads * max_splits * 128 * 4);
   if (rc == kOk) rc = dev_alloc(e, &e->part_ml, B * c->llm_heads * max_splits * 2 * 4);
+  if (rc == kOk) rc = dev_alloc(e, &e->attn_sync, B * c->llm_heads * 4);
+  if (rc == kOk) cudaMemset(e->attn_sync.p, 0, e->attn_sync.bytes);
   if (rc == kOk) rc = dev_alloc(e, &e->plan_dev, e->max_rows * 4);
   if (rc == kOk) rc = dev_alloc(e, &e->depth_sums, B * 4);
   const size_t page_halves = static_cast<size_t>(c->llm_heads) * c->kv_page_tokens * 128;
@@ -184,7 +186,7 @@ int engine_create(const vcb_config* c, int device, Engine** out) {
   if (rc == kOk) rc = dev_alloc(e, &e->counters, 16);
   if (rc == kOk) rc = dev_alloc(e, &e->sample_params, 32);
   if (rc == kOk) rc = dev_alloc(e, &e->fp_dev, 8);
-  if (rc == kOk) rc = dev_alloc(e, &e->norm_parts0, 32 * 4);
+  if (rc == kOk) rc = dev_alloc(e, &e->norm_parts0, (96 + 8) * 4);
   if (rc == kOk) rc = dev_alloc(e, &e->norm_parts_a, static_cast<size_t>(H / 16) * 32 * 4);
   if (rc == kOk) rc = dev_alloc(e, &e->norm_parts_b, static_cast<size_t>(H / 16) * 32 * 4);
   if (rc == kOk) {
@@ -213,6 +215,10 @@ int engine_create(const vcb_config* c, int device, Engine** out) {
     }
     cudaMemset(e->patch_w.p, 0, e->patch_w.bytes);
     cudaMemset(e->counters.p, 0, 16);
+    // KV pages start as zeros: the unwritten tail of a sequence's last page is multiplied by exact-zero probabilities in
+    // the prefill attention MMA, which must never meet a NaN bit pattern left over in fresh device memory
+    cudaMemset(e->k_pool.p, 0, e->k_pool.bytes);
+    cudaMemset(e->v_pool.p, 0, e->v_pool.bytes);
     for (cudaEvent_t& ev : e->stream_ev) {
       if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
         delete e;
@@ -781,7 +787,7 @@ int engine_prefill(Engine* e, const int64_t* ids, int B, int T, const void* imag
       AttnPrefillParams a;
       a.q = qkv; a.q_stride = 3 * H;
       a.k_pool = kp; a.v_pool = vp; a.block_table = e->block_table.as<int32_t>();
-      a.max_pages = e->max_pages_per_seq; a.page_tokens = c.kv_page_tokens;
+      a.max_pages = e->max_pages_per_seq; a.page_tokens = c.kv_page_tokens; a.pool_pages = e->n_pages;
       a.out = e->attn.as<__half>(); a.out_stride = H;
       a.batch = B; a.n_heads = c.llm_heads; a.seq_len = Ts; a.q_pos0 = L0; a.head_dim = 128;
       a.scale = 0.08838834764831845f;  // 1/sqrt(128)
@@ -860,12 +866,16 @@ int decode_step_launch(Engine* e, int max_ctx, cudaStream_t st) {
   static int chain_env = -1;
   if (chain_env < 0) { const char* ev = getenv("VCB_DECODE_NORM_CHAIN"); chain_env = ev ? atoi(ev) : kNormChainDefault; }
   const bool chain = chain_env != 0 && !fuse_norm && H % 64 == 0 && FF % 64 == 0;  // the TMA kernel carries the chain
-  float* parts0 = e->norm_parts0.as<float>();
+  // norm_parts0 = [rstd of the embedding rows (32) | rstd after o-proj (32) | rstd after down-proj (32) | 2 tickets]
+  float* rstd0 = e->norm_parts0.as<float>();
+  float* rstd_a = rstd0 + 32;
+  float* rstd_b = rstd0 + 64;
+  int32_t* tickets = reinterpret_cast<int32_t*>(rstd0 + 96);
   float* parts_a = e->norm_parts_a.as<float>();
   float* parts_b = e->norm_parts_b.as<float>();
-  const int nparts = H / 16;  // CTAs of a GEMM with N = H
   if (chain)
-    VCB_TRY(embed_gather_norm(e->next_ids.as<int32_t>(), e->embed.as<__half>(), x, e->llm[0].ln1.as<__half>(), xn, parts0, B, H, st));
+    VCB_TRY(embed_gather_norm(e->next_ids.as<int32_t>(), e->embed.as<__half>(), x, e->llm[0].ln1.as<__half>(), xn, rstd0,
+                              c.llm_rms_eps, B, H, st));
   else
     VCB_TRY(embed_gather(e->next_ids.as<int32_t>(), e->embed.as<__half>(), x, B, H, st));
   for (int li = 0; li < c.llm_layers; ++li) {
@@ -876,7 +886,7 @@ int decode_step_launch(Engine* e, int max_ctx, cudaStream_t st) {
     {
       SkinnyParams s;
       if (fuse_norm) { s.norm_w = l.ln1.as<__half>(); s.norm_eps = c.llm_rms_eps; }
-      if (chain) { s.cn_parts = li == 0 ? parts0 : parts_b; s.cn_nparts = li == 0 ? 1 : nparts; s.cn_eps = c.llm_rms_eps; }
+      if (chain) s.cn_rstd = li == 0 ? rstd0 : rstd_b;
       s.X = fuse_norm ? x : xn; s.ldx = H; s.W = l.qkv_w.as<__half>(); s.Wp = l.qkv_p.as<__half>(); s.Y = qkv; s.ldy = 3 * H; s.B = B; s.N = 3 * H; s.K = H;
       VCB_TRY(skinny_gemm(s, st));
     }
@@ -890,7 +900,7 @@ int decode_step_launch(Engine* e, int max_ctx, cudaStream_t st) {
       a.block_table = e->block_table.as<int32_t>(); a.max_pages = e->max_pages_per_seq; a.page_tokens = c.kv_page_tokens;
       a.ctx_len = counters + 2;  // cache_len + 1 (the current token attends to itself)
       a.max_ctx = max_ctx;
-      a.part_o = e->part_o.as<float>(); a.part_ml = e->part_ml.as<float>();
+      a.part_o = e->part_o.as<float>(); a.part_ml = e->part_ml.as<float>(); a.sync_counters = e->attn_sync.as<int32_t>();
       a.out = e->attnd.as<__half>(); a.batch = B; a.n_heads = c.llm_heads; a.scale = 0.08838834764831845f;
       VCB_TRY(attn_llama_decode(a, st));
     }
@@ -898,14 +908,14 @@ int decode_step_launch(Engine* e, int max_ctx, cudaStream_t st) {
       SkinnyParams s;
       s.X = e->attnd.as<__half>(); s.ldx = H; s.W = l.o_w.as<__half>(); s.Wp = l.o_p.as<__half>(); s.Y = x; s.ldy = H; s.residual = x; s.ldr = H;
       s.B = B; s.N = H; s.K = H;
-      if (chain) { s.pn_w = l.ln2.as<__half>(); s.pn_out = xn; s.pn_ld = H; s.pn_parts = parts_a; }
+      if (chain) { s.pn_w = l.ln2.as<__half>(); s.pn_out = xn; s.pn_ld = H; s.pn_parts = parts_a; s.pn_rstd = rstd_a; s.pn_ticket = tickets; s.pn_eps = c.llm_rms_eps; }
       VCB_TRY(skinny_gemm(s, st));
     }
     if (!fuse_norm && !chain) VCB_TRY(rmsnorm_f16(x, l.ln2.as<__half>(), xn, B, H, c.llm_rms_eps, st));
     {
       SkinnyParams s;
       if (fuse_norm) { s.norm_w = l.ln2.as<__half>(); s.norm_eps = c.llm_rms_eps; }
-      if (chain) { s.cn_parts = parts_a; s.cn_nparts = nparts; s.cn_eps = c.llm_rms_eps; }
+      if (chain) s.cn_rstd = rstd_a;
       s.X = fuse_norm ? x : xn; s.ldx = H; s.W = l.gu_w.as<__half>(); s.Wp = l.gu_p.as<__half>(); s.Y = e->midd.as<__half>(); s.ldy = FF; s.B = B; s.N = 2 * FF;
       s.K = H; s.swiglu = 1;
       VCB_TRY(skinny_gemm(s, st));
@@ -916,7 +926,7 @@ int decode_step_launch(Engine* e, int max_ctx, cudaStream_t st) {
       s.B = B; s.N = H; s.K = FF;
       if (chain) {
         s.pn_w = (li + 1 < c.llm_layers ? e->llm[li + 1].ln1 : e->final_norm).as<__half>();
-        s.pn_out = xn; s.pn_ld = H; s.pn_parts = parts_b;
+        s.pn_out = xn; s.pn_ld = H; s.pn_parts = parts_b; s.pn_rstd = rstd_b; s.pn_ticket = tickets + 1; s.pn_eps = c.llm_rms_eps;
       }
       VCB_TRY(skinny_gemm(s, st));
     }
@@ -925,7 +935,7 @@ int decode_step_launch(Engine* e, int max_ctx, cudaStream_t st) {
   {
     SkinnyParams s;
     if (fuse_norm) { s.norm_w = e->final_norm.as<__half>(); s.norm_eps = c.llm_rms_eps; }
-    if (chain) { s.cn_parts = parts_b; s.cn_nparts = nparts; s.cn_eps = c.llm_rms_eps; }
+    if (chain) s.cn_rstd = rstd_b;
     s.X = fuse_norm ? x : xn; s.ldx = H; s.W = e->lm_head.as<__half>(); s.Wp = e->lm_head_p.as<__half>(); s.Y = e->logits.as<__half>(); s.ldy = V; s.B = B; s.N = V; s.K = H;
     VCB_TRY(skinny_gemm(s, st));
   }

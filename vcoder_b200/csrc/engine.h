@@ -63,7 +63,7 @@ struct Engine {
   DevBuf pmid, feats;                             // projector
   DevBuf x, xn, qkv, attn, mid;                   // LLM prefill
   DevBuf xd, xnd, qkvd, attnd, midd;              // LLM decode (B rows)
-  DevBuf logits, next_ids, trace, part_o, part_ml, plan_dev, depth_sums;
+  DevBuf logits, next_ids, trace, part_o, part_ml, attn_sync, plan_dev, depth_sums;
   DevBuf norm_parts0, norm_parts_a, norm_parts_b;  // chained RMSNorm of the decode step: partial sum(x^2), [producer CTAs][32]
   DevBuf k_pool, v_pool, block_table, rope, counters;  // counters: [0] cache_len, [1] step
   int32_t* plan_host = nullptr;                        // pinned

@@ -514,6 +514,25 @@ int make_tmap_2d_f16(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t r
   return kOk;
 }
 
+// KV page pool [pages][heads][64 tokens][128] viewed as [n_rows = pages*heads][64][128]: box = one 64-wide head_dim half
+// of one page of one head (64 tokens x 128 B = 8 KiB, 128B-swizzled) for the tcgen05 prefill attention
+int make_tmap_pages_f16(CUtensorMap* m, const void* ptr, uint64_t n_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  VCB_CHECK(fn != nullptr, kErrCuda, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[3] = {128, 64, n_rows};
+  cuuint64_t strides[2] = {256, 64 * 256};
+  cuuint32_t box[3] = {64, 64, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_thread_error("cuTensorMapEncodeTiled (KV page map) failed with CUresult " + std::to_string(static_cast<int>(r)));
+    return kErrCuda;
+  }
+  return kOk;
+}
+
 // W [N, K] row-major viewed as [K/64][N][64] for the TMA-fed skinny GEMM: box = 4 k-blocks x 16 rows x 64 k (8 KiB)
 int make_tmap_w3d(CUtensorMap* m, const void* ptr, uint64_t K, uint64_t N, uint32_t box_kblocks) {
   EncodeTiledFn fn = get_encode_fn();

@@ -18,6 +18,7 @@ struct AttnPrefillParams {
   const int32_t* block_table = nullptr;  // [batch][max_pages]
   int max_pages = 0;
   int page_tokens = 0;
+  int pool_pages = 0;     // pages in the pools (sizes the TMA view of the tcgen05 kernel); 0 = unknown
   __half* out = nullptr;  // [B*S, heads*head_dim]
   long out_stride = 0;
   int batch = 0, n_heads = 0, seq_len = 0, head_dim = 0;
@@ -30,7 +31,8 @@ int attn_vit(const AttnPrefillParams& p, cudaStream_t stream);       // dispatch
 int attn_vit_tc5(const AttnPrefillParams& p, cudaStream_t stream);   // tcgen05 + TMEM (attn_vit_tc5.cu)
 int attn_vit_legacy(const AttnPrefillParams& p, cudaStream_t stream);  // mma.sync flash attention
 int attn_vit_pair(const AttnPrefillParams& p, cudaStream_t stream);    // tcgen05, two query tiles per CTA (attn_vit_pair.cu)
-int attn_llama_prefill(const AttnPrefillParams& p, cudaStream_t stream);
+int attn_llama_prefill(const AttnPrefillParams& p, cudaStream_t stream);       // dispatcher (VCB_PREFILL_ATTN=tc5|legacy)
+int attn_llama_prefill_tc5(const AttnPrefillParams& p, cudaStream_t stream);   // tcgen05 + TMEM + TMA (attn_prefill_tc5.cu)
 
 struct AttnDecodeParams {
   const __half* q = nullptr;  // [B, 3H] (rotated q in the first H columns), stride q_stride
@@ -49,6 +51,7 @@ struct AttnDecodeParams {
   float* part_o = nullptr;           // [B*heads, splits, 128]
   float* part_ml = nullptr;          // [B*heads, splits, 2]
   __half* out = nullptr;             // [B, H]
+  int32_t* sync_counters = nullptr;  // [B*heads] zero-initialised arrival counters (last-CTA merge of the bulk-copy kernel)
   int batch = 0, n_heads = 0;
   int prefetch = 0;  // L2-prefetch the split's KV pages before the grid-dependency wait (VCB_ATTN_DEC_PF)
   float scale = 1.f;
@@ -81,16 +84,18 @@ struct SkinnyParams {
   float norm_eps = 0.f;
   // RMSNorm chained through the GEMMs of a decode step (no norm kernel in between), TMA kernel only:
   //  producer side (o-proj / down-proj, Y = new residual stream x): also emits the NEXT norm's weighted input
-  //    pn_out[b, c] = fp16(x[b, c] * pn_w[c]) and this CTA's share of sum(x^2): pn_parts[blockIdx.x * 32 + b]
-  //  consumer side (qkv / gate|up / lm_head): X is such a weighted input; the accumulators are scaled by
-  //    rsqrt(sum over cn_nparts partial sums / K + cn_eps) in the epilogue (summed in a fixed order: deterministic)
+  //    pn_out[b, c] = fp16(x[b, c] * pn_w[c]) and this CTA's share of sum(x^2) (pn_parts[blockIdx.x * 32 + b]); the CTA
+  //    that finishes last folds the shares into pn_rstd[b] = rsqrt(mean(x^2) + pn_eps) (pn_ticket: zeroed arrival counter)
+  //  consumer side (qkv / gate|up / lm_head): X is such a weighted input; the fp32 accumulators are scaled by cn_rstd[b]
+  //    in the epilogue
   const __half* pn_w = nullptr;
   __half* pn_out = nullptr;
   long pn_ld = 0;
   float* pn_parts = nullptr;
-  const float* cn_parts = nullptr;
-  int cn_nparts = 0;
-  float cn_eps = 0.f;
+  float* pn_rstd = nullptr;
+  int32_t* pn_ticket = nullptr;
+  float pn_eps = 0.f;
+  const float* cn_rstd = nullptr;
   unsigned long long* trace = nullptr;  // timeline slots (common.h trace_slots), else null
 };
 int skinny_gemm(const SkinnyParams& p, cudaStream_t stream);
@@ -114,9 +119,9 @@ int rope_kv_write(__half* qkv, int B, int T, int H, int n_heads, const float2* c
 int splice_gather(const int32_t* plan, const __half* embed, const __half* feats, __half* out, long rows, int H,
                   cudaStream_t s);
 int embed_gather(const int32_t* ids, const __half* embed, __half* out, int B, int H, cudaStream_t s);
-// embed_gather + the first RMSNorm's producer half: out = embed[ids], xn_out = fp16(out * norm_w), parts[b] = sum(out[b]^2)
+// embed_gather + the first RMSNorm's producer half: out = embed[ids], xn_out = fp16(out * norm_w), rstd[b] = rsqrt(mean(out[b]^2) + eps)
 int embed_gather_norm(const int32_t* ids, const __half* embed, __half* out, const __half* norm_w, __half* xn_out,
-                      float* parts, int B, int H, cudaStream_t s);
+                      float* rstd, float eps, int B, int H, cudaStream_t s);
 // first-index argmax over fp16 logits [B,V]; writes next[b] and (optionally) trace[b*trace_stride + *step]
 int argmax_rows(const __half* logits, int B, int V, int32_t* next, int32_t* trace, int trace_stride,
                 const int32_t* step_dev, cudaStream_t s);

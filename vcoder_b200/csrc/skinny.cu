@@ -245,7 +245,7 @@ int skinny_gemm_tc5(const SkinnyParams& p, cudaStream_t stream);
 bool skinny_tc5_supported(const SkinnyParams& p);
 
 int skinny_gemm(const SkinnyParams& p, cudaStream_t stream) {
-  if (p.pn_parts != nullptr || p.cn_parts != nullptr) {  // the chained RMSNorm lives in the TMA kernel only
+  if (p.pn_parts != nullptr || p.cn_rstd != nullptr) {  // the chained RMSNorm lives in the TMA kernel only
     VCB_CHECK(p.K % 64 == 0, kErrInvalid, "skinny_gemm: the chained RMSNorm needs K % 64 == 0");
     return skinny_gemm_tma(p, stream);
   }

@@ -170,22 +170,9 @@ skinny_tma_kernel(const __grid_constant__ CUtensorMap tmW, SkinnyParams p) {
 
   uint4 xv[2 * kGroup][NB], xnext[2 * kGroup][NB];
   if (my_groups > 0) load_x(0, xv);
-  // chained RMSNorm, consumer half: every thread sums a fixed subset of the producer CTAs' partial sum(x^2) — the loads
-  // travel together with the first X fragments
-  float cn[CHAIN ? 8 * NB : 1];
-#pragma unroll
-  for (int j = 0; j < (CHAIN ? 8 * NB : 1); ++j) cn[j] = 0.f;
-  const bool chain_in = CHAIN && p.cn_parts != nullptr;  // CHAIN = false: the instantiation every other caller gets
-  if (chain_in) {
-    for (int part = tid; part < p.cn_nparts; part += WARPS * 32) {
-      const float4* q = reinterpret_cast<const float4*>(p.cn_parts + static_cast<long>(part) * 32);
-#pragma unroll
-      for (int j = 0; j < 2 * NB; ++j) {
-        const float4 v = q[j];
-        cn[4 * j] += v.x; cn[4 * j + 1] += v.y; cn[4 * j + 2] += v.z; cn[4 * j + 3] += v.w;
-      }
-    }
-  }
+  // chained RMSNorm, consumer half: X is fp16(x * w_norm); rstd[b] was finalised by the producer's last CTA and scales the
+  // fp32 accumulators in the epilogue (nothing extra in the streaming loop)
+  const bool chain_in = CHAIN && p.cn_rstd != nullptr;  // CHAIN = false: the instantiation every other caller gets
   for (int i = 0; i < my_groups; ++i) {
     const int s = i % kDepth;
     const uint32_t ph = static_cast<uint32_t>((i / kDepth) & 1);
@@ -245,23 +232,15 @@ skinny_tma_kernel(const __grid_constant__ CUtensorMap tmW, SkinnyParams p) {
       v += __shfl_xor_sync(0xffffffffu, v, 2);
       if (t == 0) s_ssq[warp * 8 * NB + nb * 8 + g] = v;
     }
-  } else if (chain_in) {
-#pragma unroll
-    for (int j = 0; j < (CHAIN ? 8 * NB : 1); ++j) {
-      float v = cn[j];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) s_ssq[warp * 8 * NB + j] = v;
-    }
   }
   __syncthreads();
-  const float norm_eps = fuse_norm ? p.norm_eps : p.cn_eps;
   auto rstd_of = [&](int n) -> float {
-    if (!fuse_norm && !chain_in) return 1.f;
+    if (chain_in) return __ldcg(p.cn_rstd + n);
+    if (!fuse_norm) return 1.f;
     float v = 0.f;
 #pragma unroll
     for (int w = 0; w < WARPS; ++w) v += s_ssq[w * 8 * NB + n];
-    return rsqrtf(v / static_cast<float>(p.K) + norm_eps);
+    return rsqrtf(v / static_cast<float>(p.K) + p.norm_eps);
   };
   constexpr int kThreads = WARPS * 32;
   if (p.swiglu) {
@@ -306,6 +285,33 @@ skinny_tma_kernel(const __grid_constant__ CUtensorMap tmW, SkinnyParams p) {
         if (r == 0 && n < 32) p.pn_parts[static_cast<long>(blockIdx.x) * 32 + n] = sq;
       }
     }
+    if (chain_out) {
+      // The CTA that draws the last ticket folds every CTA's partial sum(x^2) (fixed order: deterministic) into
+      // rstd[b] = rsqrt(mean(x^2) + eps): the RMSNorm statistic is complete when this kernel is, no norm kernel follows.
+      __threadfence();
+      __syncthreads();
+      int* s_tk = reinterpret_cast<int*>(s_ssq);
+      if (tid == 0) *s_tk = atomicAdd(p.pn_ticket, 1);
+      __syncthreads();
+      if (*s_tk == static_cast<int>(gridDim.x) - 1) {
+        __threadfence();
+        float* sred = reinterpret_cast<float*>(red);  // the split-K buffers are dead: [WARPS][32] floats
+        const int n = tid & 31, chunk = tid >> 5;
+        float v = 0.f;
+        if (n < p.B)
+          for (int c = chunk; c < static_cast<int>(gridDim.x); c += WARPS) v += __ldcg(p.pn_parts + static_cast<long>(c) * 32 + n);
+        __syncthreads();
+        sred[chunk * 32 + n] = v;
+        __syncthreads();
+        if (tid < p.B) {
+          float tot = 0.f;
+#pragma unroll
+          for (int w = 0; w < WARPS; ++w) tot += sred[w * 32 + tid];
+          p.pn_rstd[tid] = rsqrtf(tot / static_cast<float>(p.N) + p.pn_eps);
+        }
+        if (tid == 0) *p.pn_ticket = 0;  // ready for the next launch (stream-ordered)
+      }
+    }
   }
   trace_mark(p.trace, blockIdx.x, 2);
 }
@@ -328,7 +334,7 @@ template <int NB>
 int launch_packed(const SkinnyParams& p, int grid, int depth, cudaStream_t stream) {
   CUtensorMap unused;
   memset(&unused, 0, sizeof(unused));
-  if (p.pn_parts != nullptr || p.cn_parts != nullptr) return launch_tma<NB, 4, 2, 4, true, true>(unused, p, grid, stream);
+  if (p.pn_parts != nullptr || p.cn_rstd != nullptr) return launch_tma<NB, 4, 2, 4, true, true>(unused, p, grid, stream);
   if (depth >= 3) return launch_tma<NB, 4, 3, 4, true>(unused, p, grid, stream);
   return launch_tma<NB, 4, 2, 4, true>(unused, p, grid, stream);
 }
@@ -349,7 +355,7 @@ template <int NB>
 int launch_tma_w(const CUtensorMap& tm, const SkinnyParams& p, int grid, int warps, int depth, int group,
                  cudaStream_t stream) {
   // the chained RMSNorm (opt-in experiment) exists for the default ring shape only
-  if (p.pn_parts != nullptr || p.cn_parts != nullptr) return launch_tma<NB, 4, 2, 4, false, true>(tm, p, grid, stream);
+  if (p.pn_parts != nullptr || p.cn_rstd != nullptr) return launch_tma<NB, 4, 2, 4, false, true>(tm, p, grid, stream);
   if (group == 2) {
     if (depth <= 2) return launch_tma<NB, 4, 2, 2>(tm, p, grid, stream);
     if (depth == 3) return launch_tma<NB, 4, 3, 2>(tm, p, grid, stream);
@@ -457,7 +463,7 @@ int skinny_gemm_tma(const SkinnyParams& p_in, cudaStream_t stream) {
       if (u.warps > 0) warps = u.warps;
       if (u.depth > 0) depth = u.depth;
     }
-  if (p.pn_parts != nullptr || p.cn_parts != nullptr) group = 4;
+  if (p.pn_parts != nullptr || p.cn_rstd != nullptr) { group = 4; warps = 4; depth = 2; }
   CUtensorMap tm;
   VCB_TRY(make_tmap_w3d(&tm, p.W, p.K, p.N, group));
   p.trace = trace_slots(kTraceSkinny, grid, p.N);

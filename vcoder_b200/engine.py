@@ -101,8 +101,8 @@ class Engine:
             raise ValueError(f"{what}: expected [n, 3, {S}, {S}] (the tower's image size), got {tuple(t.shape)}")
         if batch is not None and t.shape[0] != batch:
             raise ValueError(f"{what}: {t.shape[0]} images for a batch of {batch} sequences")
-        if batch is None and not 1 <= t.shape[0] <= 3 * self.max_batch:
-            raise ValueError(f"{what}: {t.shape[0]} images, this handle takes 1..{3 * self.max_batch} per call")
+        if batch is None and t.shape[0] < 1:
+            raise ValueError(f"{what}: empty image batch")
 
     def tower_forward(self, pixels: torch.Tensor) -> torch.Tensor:
         px = _as_half_any(pixels)
