@@ -562,7 +562,7 @@ def run_b200(args):
         line = {
             "metric": METRIC if headline else f"end-to-end tokens/sec (prefill+decode) VCoder-DS-{args.preset.upper()} bs{args.batch}",
             "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f16", "data": "synthetic", "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * N * 4,
                     "ms_per_step": ms_e2e / args.steps},
@@ -585,9 +585,18 @@ def main():
     ap.add_argument("--preset", default="7b")
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--new-tokens", type=int, default=128)
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="strong scaling: fixed global batch split over the ranks (overrides --batch; reported as scaling=strong)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-library-baseline", action="store_true")
     args = ap.parse_args()
+    args.scaling = "weak"
+    if args.global_batch > 0:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if args.global_batch % world != 0:
+            raise SystemExit(f"--global-batch {args.global_batch} is not divisible by {world} ranks")
+        args.batch = args.global_batch // world
+        args.scaling = "strong"
     if args.impl == "reference":
         run_reference(args)
     else:

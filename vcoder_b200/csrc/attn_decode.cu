@@ -17,7 +17,7 @@
 namespace vcb {
 namespace {
 
-constexpr int kChunk = 256;  // keys per split
+constexpr int kChunk = 256;  // default keys per split (AttnDecodeParams::chunk; VCB_ATTN_DEC_CHUNK = 128 | 256 | 512)
 constexpr int kPT = 64;      // tokens per KV page (checked on the host)
 constexpr int kDecThreads = 128;
 constexpr int kDH = 128;
@@ -67,8 +67,8 @@ __device__ __forceinline__ void merge_by_last_cta(const AttnDecodeParams& p, int
 // CLUSTER = true: the `splits` CTAs of one (sequence, head) form a thread-block cluster; the partial (max, sum, acc) states
 // stay in shared memory and CTA 0 of the cluster merges them through distributed shared memory and writes the fp16 output
 // itself — no partial buffers in HBM, no combine kernel (one launch and one dependency boundary less per layer).
-template <bool CLUSTER>
-__global__ void __launch_bounds__(kDecThreads)
+template <bool CLUSTER, int MINB>
+__global__ void __launch_bounds__(kDecThreads, MINB)
 attn_decode_split_kernel(AttnDecodeParams p, int splits) {
   __shared__ float s_acc[8][kDH];
   __shared__ float s_m[8], s_l[8];
@@ -79,13 +79,13 @@ attn_decode_split_kernel(AttnDecodeParams p, int splits) {
   trace_mark(p.trace, cta_lin, 0);
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x, hw = tid >> 4, l16 = tid & 15;
-  const int k0 = split * kChunk;
+  const int k0 = split * p.chunk;
   if (p.prefetch && tid == 0) {
     // While the QKV GEMM drains: pull this split's K/V pages (16 KiB contiguous per page and head, written in earlier
     // steps) into L2.  The context length read here may still be the previous step's — a lower bound is all this needs.
     const int ctx0 = *reinterpret_cast<const volatile int32_t*>(p.ctx_len);
     if (k0 < ctx0) {
-      const int nt = (min(kChunk, ctx0 - k0) + kPT - 1) / kPT;
+      const int nt = (min(p.chunk, ctx0 - k0) + kPT - 1) / kPT;
       const int32_t* bt0 = p.block_table + b * p.max_pages + k0 / kPT;
       for (int t = 0; t < nt; ++t) {
         const long off = (static_cast<long>(bt0[t]) * p.n_heads + h) * kPT * kDH;
@@ -109,7 +109,7 @@ attn_decode_split_kernel(AttnDecodeParams p, int splits) {
     }
     return;
   }
-  const int nkeys = min(kChunk, ctx - k0);
+  const int nkeys = min(p.chunk, ctx - k0);
 
   // Fused RoPE (p.cos_sin != null): q arrives un-rotated, and the current token's k / v are taken from the QKV row,
   // rotated here and appended to the paged cache by the one CTA whose split contains the current position
@@ -142,7 +142,7 @@ attn_decode_split_kernel(AttnDecodeParams p, int splits) {
   }
   const int32_t* bt = p.block_table + b * p.max_pages + k0 / kPT;
   // where the current token lives inside this split (only meaningful when pos is in [k0, k0 + nkeys))
-  const bool own_pos = fuse_rope && pos >= k0 && pos < k0 + kChunk;
+  const bool own_pos = fuse_rope && pos >= k0 && pos < k0 + p.chunk;
   const int pos_tile = (pos - k0) / kPT, pos_slot = (pos - k0) % kPT;
 
   float m = -INFINITY, l = 0.f;
@@ -465,22 +465,38 @@ attn_decode_tma_kernel(AttnDecodeParams p, int splits) {
 }  // namespace
 
 namespace {
-// VCB_ATTN_DEC: "ldg" (default) register-staged split kernel whose last CTA merges the partials; "ldg2" the same split
-// kernel + a separate combine kernel (round 1); "tma" the bulk-copy fed kernel (measured slower at B = 8, ctx 1271: 46 vs
-// 33 us per layer — a CTA loads its 64 KiB, computes and leaves, so its shared memory carries no loads during the tail)
+// VCB_ATTN_DEC: default = register-staged split kernel + combine kernel.  "merge": the same split kernel whose last CTA per
+// (sequence, head) merges the partials (threadfence + ticket): measured SLOWER (38.9 vs 33.3 + 2.4 + 0.6 us per layer at
+// B = 8, ctx 1271; profiles/r02_trace_decode_merge_last_cta.csv) — the fence + atomic tail of 1536 CTAs costs more than one
+// small launch.  "tma": the bulk-copy fed kernel, also slower (46 us: a CTA loads its 64 KiB, computes and leaves, so its
+// shared memory carries no loads during the tail).
 int decode_attn_impl() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("VCB_ATTN_DEC");
-    v = (e == nullptr) ? 0 : (e[0] == 't' ? 2 : (e[0] == 'l' && e[1] == 'd' && e[2] == 'g' && e[3] == '2') ? 1 : 0);
+    v = (e == nullptr) ? 1 : (e[0] == 't' ? 2 : (e[0] == 'm' ? 0 : 1));
   }
   return v;
 }
 bool decode_attn_ldg() { return decode_attn_impl() != 2; }
+int decode_attn_chunk() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("VCB_ATTN_DEC_CHUNK");
+    const int c = e ? atoi(e) : kChunk;
+    v = (c == 128 || c == 512) ? c : kChunk;
+  }
+  return v;
+}
+int decode_attn_minb() {  // resident CTAs per SM the split kernel is compiled for (register cap 168 vs 128)
+  static int v = 0;
+  if (v == 0) { const char* e = getenv("VCB_ATTN_DEC_MINB"); v = (e && atoi(e) == 4) ? 4 : 3; }
+  return v;
+}
 }  // namespace
 
 int attn_decode_splits(int max_ctx) {
-  const int chunk = decode_attn_ldg() ? kChunk : kChunkT;
+  const int chunk = decode_attn_ldg() ? decode_attn_chunk() : kChunkT;
   return (max_ctx + chunk - 1) / chunk;
 }
 
@@ -489,6 +505,7 @@ int attn_llama_decode(const AttnDecodeParams& p_in, cudaStream_t stream) {
   static int env_pf = -1;  // VCB_ATTN_DEC_PF=0 turns off: L2-prefetch the split's KV pages before the grid-dependency wait
   if (env_pf < 0) { const char* e = getenv("VCB_ATTN_DEC_PF"); env_pf = e ? atoi(e) : 1; }  // measured: DESIGN.md section 3.1
   p.prefetch = env_pf;
+  p.chunk = decode_attn_chunk();
   const int splits = attn_decode_splits(p.max_ctx);
   VCB_CHECK(splits >= 1, kErrInvalid, "attn_llama_decode: empty context");
   VCB_CHECK(p.page_tokens == kPT, kErrInvalid, "attn_llama_decode: KV page must hold 64 tokens");
@@ -527,18 +544,19 @@ int attn_llama_decode(const AttnDecodeParams& p_in, cudaStream_t stream) {
     at[1].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 2;
-    VCB_CUDA(cudaLaunchKernelEx(&cfg, attn_decode_split_kernel<true>, p, splits));
+    VCB_CUDA(cudaLaunchKernelEx(&cfg, attn_decode_split_kernel<true, 3>, p, splits));
     return kOk;
   }
+  auto split_kernel = decode_attn_minb() == 4 ? attn_decode_split_kernel<false, 4> : attn_decode_split_kernel<false, 3>;
   if (decode_attn_impl() == 0 && p.sync_counters != nullptr) {  // one kernel: the last CTA of a (sequence, head) merges
     KernelScope scope(kCatAttnDecode, stream, 1);
-    VCB_CUDA(launch_pdl(attn_decode_split_kernel<false>, grid, dim3(kDecThreads), 0, stream, p, splits));
+    VCB_CUDA(launch_pdl(split_kernel, grid, dim3(kDecThreads), 0, stream, p, splits));
     return kOk;
   }
   p.sync_counters = nullptr;
   p.trace2 = trace_slots(kTraceAttnCombine, p.batch * p.n_heads, splits);
   KernelScope scope(kCatAttnDecode, stream, 2);
-  VCB_CUDA(launch_pdl(attn_decode_split_kernel<false>, grid, dim3(kDecThreads), 0, stream, p, splits));
+  VCB_CUDA(launch_pdl(split_kernel, grid, dim3(kDecThreads), 0, stream, p, splits));
   VCB_CUDA(launch_pdl(attn_decode_combine_kernel, dim3(p.batch * p.n_heads), dim3(kDH), 0, stream, p, splits));
   return kOk;
 }

@@ -15,6 +15,8 @@
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
+#include <map>
+#include <tuple>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -404,8 +406,41 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// Descriptor cache: a prefill issues ~450 GEMMs over a few dozen distinct (pointer, shape) pairs — workspaces and weights
+// live at fixed addresses for the life of a handle — so every tensor map is encoded by the driver once and then reused.
+struct TmapKey {
+  const void* ptr;
+  uint64_t a, b, c;
+  uint32_t box0, box1, kind;
+  bool operator<(const TmapKey& o) const {
+    return std::tie(ptr, a, b, c, box0, box1, kind) < std::tie(o.ptr, o.a, o.b, o.c, o.box0, o.box1, o.kind);
+  }
+};
+std::map<TmapKey, CUtensorMap>& tmap_cache() {
+  static std::map<TmapKey, CUtensorMap> c;
+  return c;
+}
+std::mutex& tmap_mu() {
+  static std::mutex m;
+  return m;
+}
+bool tmap_lookup(const TmapKey& k, CUtensorMap* out) {
+  std::lock_guard<std::mutex> lk(tmap_mu());
+  auto it = tmap_cache().find(k);
+  if (it == tmap_cache().end()) return false;
+  *out = it->second;
+  return true;
+}
+void tmap_store(const TmapKey& k, const CUtensorMap& m) {
+  std::lock_guard<std::mutex> lk(tmap_mu());
+  if (tmap_cache().size() > 8192) tmap_cache().clear();  // op-level callers with ever-new buffers
+  tmap_cache()[k] = m;
+}
+
 int make_tmap_kmajor(CUtensorMap* m, const void* ptr, uint64_t k, uint64_t rows, uint64_t ld_elems,
                      uint32_t box_rows) {
+  const TmapKey key{ptr, k, rows, ld_elems, BK, box_rows, 0};
+  if (tmap_lookup(key, m)) return kOk;
   EncodeTiledFn fn = get_encode_fn();
   VCB_CHECK(fn != nullptr, kErrCuda, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[2] = {k, rows};
@@ -419,6 +454,7 @@ int make_tmap_kmajor(CUtensorMap* m, const void* ptr, uint64_t k, uint64_t rows,
     set_thread_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
     return kErrCuda;
   }
+  tmap_store(key, *m);
   return kOk;
 }
 
@@ -498,6 +534,8 @@ int launch_pair_act(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEp
 // generic 2-D fp16 tensor map with the 128-byte swizzle (box_inner must be 64 elements = 128 bytes)
 int make_tmap_2d_f16(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows, uint64_t ld_elems, uint32_t box_inner,
                      uint32_t box_rows) {
+  const TmapKey key{ptr, inner, rows, ld_elems, box_inner, box_rows, 1};
+  if (tmap_lookup(key, m)) return kOk;
   EncodeTiledFn fn = get_encode_fn();
   VCB_CHECK(fn != nullptr, kErrCuda, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[2] = {inner, rows};
@@ -511,12 +549,15 @@ int make_tmap_2d_f16(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t r
     set_thread_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
     return kErrCuda;
   }
+  tmap_store(key, *m);
   return kOk;
 }
 
 // KV page pool [pages][heads][64 tokens][128] viewed as [n_rows = pages*heads][64][128]: box = one 64-wide head_dim half
 // of one page of one head (64 tokens x 128 B = 8 KiB, 128B-swizzled) for the tcgen05 prefill attention
 int make_tmap_pages_f16(CUtensorMap* m, const void* ptr, uint64_t n_rows) {
+  const TmapKey key{ptr, n_rows, 0, 0, 64, 64, 2};
+  if (tmap_lookup(key, m)) return kOk;
   EncodeTiledFn fn = get_encode_fn();
   VCB_CHECK(fn != nullptr, kErrCuda, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[3] = {128, 64, n_rows};
@@ -530,11 +571,14 @@ int make_tmap_pages_f16(CUtensorMap* m, const void* ptr, uint64_t n_rows) {
     set_thread_error("cuTensorMapEncodeTiled (KV page map) failed with CUresult " + std::to_string(static_cast<int>(r)));
     return kErrCuda;
   }
+  tmap_store(key, *m);
   return kOk;
 }
 
 // W [N, K] row-major viewed as [K/64][N][64] for the TMA-fed skinny GEMM: box = 4 k-blocks x 16 rows x 64 k (8 KiB)
 int make_tmap_w3d(CUtensorMap* m, const void* ptr, uint64_t K, uint64_t N, uint32_t box_kblocks) {
+  const TmapKey key{ptr, K, N, 0, box_kblocks, 16, 3};
+  if (tmap_lookup(key, m)) return kOk;
   EncodeTiledFn fn = get_encode_fn();
   VCB_CHECK(fn != nullptr, kErrCuda, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[3] = {64, N, K / 64};
@@ -548,6 +592,7 @@ int make_tmap_w3d(CUtensorMap* m, const void* ptr, uint64_t K, uint64_t N, uint3
     set_thread_error("cuTensorMapEncodeTiled (3-D weight map) failed with CUresult " + std::to_string(static_cast<int>(r)));
     return kErrCuda;
   }
+  tmap_store(key, *m);
   return kOk;
 }
 

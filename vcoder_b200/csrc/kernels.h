@@ -54,6 +54,7 @@ struct AttnDecodeParams {
   int32_t* sync_counters = nullptr;  // [B*heads] zero-initialised arrival counters (last-CTA merge of the bulk-copy kernel)
   int batch = 0, n_heads = 0;
   int prefetch = 0;  // L2-prefetch the split's KV pages before the grid-dependency wait (VCB_ATTN_DEC_PF)
+  int chunk = 256;   // keys per flash-decoding split (register-staged kernel)
   float scale = 1.f;
   unsigned long long* trace = nullptr;   // timeline slots of the split kernel (common.h trace_slots), else null
   unsigned long long* trace2 = nullptr;  // ... of the combine kernel
@@ -74,6 +75,7 @@ struct SkinnyParams {
   long ldr = 0;
   int B = 0, N = 0, K = 0;
   int swiglu = 0;  // W rows 8/8 interleaved gate|up; N_out = N/2
+  int tpc = 1;     // multi-tile kernel (skinny_stream.cu): consecutive 16-row tiles per CTA (set by the launcher)
   int mode = 1;    // chunk->warp mapping (see skinny.cu)
   int prefetch = 0;  // cp.async.bulk.prefetch.L2 ahead of the demand loads (measured slower: off)
   int pf_groups = 0;  // TMA kernel: k-groups per warp prefetched into L2 before the grid-dependency wait (first wave only)
@@ -100,6 +102,7 @@ struct SkinnyParams {
 };
 int skinny_gemm(const SkinnyParams& p, cudaStream_t stream);
 int tune_skinny(int N, int K, int warps, int depth);  // ring shape of the TMA kernel for one (N, K); 0 = default
+int skinny_gemm_stream(const SkinnyParams& p, cudaStream_t stream);  // balanced multi-tile TMA kernel (skinny_stream.cu): the default
 int skinny_gemm_tma(const SkinnyParams& p, cudaStream_t stream);  // TMA / bulk-copy fed kernel (skinny_tma.cu); needs K % 64 == 0
 // W[N,K] row-major -> the streaming layout of the decode GEMM: [N/16][K/64][16 rows][128 B, 16-byte chunks pre-swizzled]
 int pack_skinny_weights(const __half* W, __half* Wp, int N, int K, cudaStream_t stream);

@@ -250,13 +250,16 @@ int skinny_gemm(const SkinnyParams& p, cudaStream_t stream) {
     return skinny_gemm_tma(p, stream);
   }
   {
-    static int impl = -1;  // 0 = LDG kernel (this file), 1 = TMA-fed mma.sync kernel (skinny_tma.cu), 2 = tcgen05 (skinny_tc5.cu)
+    // 0 = LDG kernel (this file), 1 = TMA-fed mma.sync kernel, one CTA per tile (skinny_tma.cu), 2 = tcgen05 (skinny_tc5.cu),
+    // 3 = TMA-fed, balanced multi-tile CTAs (skinny_stream.cu; default; bit-identical to 1)
+    static int impl = -1;
     if (impl < 0) {
       const char* e = getenv("VCB_SKINNY_IMPL");
       const std::string v = e ? e : "";
-      impl = v == "ldg" ? 0 : (v == "tc5" ? 2 : 1);
+      impl = v == "ldg" ? 0 : (v == "tc5" ? 2 : (v == "tma" ? 1 : 3));
     }
     if (impl == 2 && skinny_tc5_supported(p)) return skinny_gemm_tc5(p, stream);
+    if (impl == 3 && p.K % 64 == 0 && p.norm_w == nullptr && p.Wp == nullptr) return skinny_gemm_stream(p, stream);
     if (impl >= 1 && p.K % 64 == 0) return skinny_gemm_tma(p, stream);
   }
   VCB_CHECK(p.B >= 1 && p.B <= 32, kErrInvalid, "skinny_gemm: batch must be in [1, 32]");
