@@ -18,3 +18,6 @@ for warps in (4, 8, 16, 32):
     for fma in (0, 1):
         _lib.check(lib.vcb_microbench(1, warps, fma, 4000, C.byref(r)))
         print(json.dumps({"bench": "ex2", "warps": warps, "with_fma": fma, "ex2_per_clk_per_sm": round(r.value, 2)}))
+for warps in (4, 8, 16):
+    _lib.check(lib.vcb_microbench(2, warps, 0, 4000, C.byref(r)))
+    print(json.dumps({"bench": "ex2_f16x2", "warps": warps, "ex2_per_clk_per_sm": round(r.value, 2)}))

@@ -16,10 +16,10 @@ for _ in range(3):
     lib.vcb_op_attention_vit_f16(_lib.ptr(qkv), B, S, heads, 0.125, _lib.ptr(o), None)
 torch.cuda.synchronize()
 d = dbg.cpu()
-t0 = int(d[128])
-print("cta cycles", int(d[129]) - t0)
-names = ["blk_start", "S_ready", "S_loaded", "max_done", "PVprev_done", "rescaled", "exp_P_done", "P_arrived"]
+t0 = int(d[240])
+print("cta cycles", int(d[241]) - t0)
+names = ["half_start", "S_ready", "S_loaded", "max_done", "Pbuf_free", "rescaled", "exp_P_done", "P_arrived"]
 for t in range(2):
     print("tile", "AB"[t], " ".join(f"{n:>12s}" for n in names))
-    for j in range(5):
-        print("   ", j, " ".join(f"{int(d[(t * 8 + j) * 8 + k]) - t0:12d}" for k in range(8)))
+    for n in range(10):
+        print("   ", n, " ".join(f"{int(d[(t * 10 + n) * 8 + k]) - t0:12d}" for k in range(8)))

@@ -23,6 +23,10 @@ INCLUDE = PKG.parent / "include"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-I", str(INCLUDE), "-I", str(CSRC)]
+# VCB_EXPERIMENTAL=1 at build time also compiles the A/B variants that were measured and rejected (packed weight stream,
+# ring-shape sweep, tcgen05 skinny GEMM, one-tile ViT attention, bulk-copy / cluster decode attention): DESIGN.md section 3.3
+if os.environ.get("VCB_EXPERIMENTAL", "0") not in ("", "0"):
+    CFLAGS.append("-DVCB_EXPERIMENTAL=1")
 
 
 def _digest(paths) -> str:

@@ -286,6 +286,7 @@ attn_decode_combine_kernel(AttnDecodeParams p, int splits) {
 }
 
 
+#ifdef VCB_EXPERIMENTAL
 // ------------------------------------------------------------------------------------------------------------------
 // Bulk-copy fed variant (default).  One CTA = (128-key split, head, sequence): the split's two K pages and two V pages
 // (16 KiB contiguous each: one page of one head) are fetched by four cp.async.bulk copies issued BEFORE the
@@ -462,6 +463,8 @@ attn_decode_tma_kernel(AttnDecodeParams p, int splits) {
   trace_mark(p.trace, cta_lin, 2);
 }
 
+#endif  // VCB_EXPERIMENTAL
+
 }  // namespace
 
 namespace {
@@ -496,7 +499,11 @@ int decode_attn_minb() {  // resident CTAs per SM the split kernel is compiled f
 }  // namespace
 
 int attn_decode_splits(int max_ctx) {
+#ifdef VCB_EXPERIMENTAL
   const int chunk = decode_attn_ldg() ? decode_attn_chunk() : kChunkT;
+#else
+  const int chunk = decode_attn_chunk();
+#endif
   return (max_ctx + chunk - 1) / chunk;
 }
 
@@ -510,6 +517,7 @@ int attn_llama_decode(const AttnDecodeParams& p_in, cudaStream_t stream) {
   VCB_CHECK(splits >= 1, kErrInvalid, "attn_llama_decode: empty context");
   VCB_CHECK(p.page_tokens == kPT, kErrInvalid, "attn_llama_decode: KV page must hold 64 tokens");
   dim3 grid(splits, p.n_heads, p.batch);
+#ifdef VCB_EXPERIMENTAL
   if (!decode_attn_ldg()) {
     VCB_CHECK(p.sync_counters != nullptr, kErrInvalid, "attn_llama_decode: sync_counters missing");
     static bool attr = false;
@@ -547,6 +555,7 @@ int attn_llama_decode(const AttnDecodeParams& p_in, cudaStream_t stream) {
     VCB_CUDA(cudaLaunchKernelEx(&cfg, attn_decode_split_kernel<true, 3>, p, splits));
     return kOk;
   }
+#endif  // VCB_EXPERIMENTAL (bulk-copy fed and cluster variants: measured slower)
   auto split_kernel = decode_attn_minb() == 4 ? attn_decode_split_kernel<false, 4> : attn_decode_split_kernel<false, 3>;
   if (decode_attn_impl() == 0 && p.sync_counters != nullptr) {  // one kernel: the last CTA of a (sequence, head) merges
     KernelScope scope(kCatAttnDecode, stream, 1);

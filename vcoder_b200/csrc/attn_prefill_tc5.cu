@@ -7,11 +7,11 @@
 // operand straight out of the page pool ([page][head][64 tokens][128] viewed as a 3-D tensor, 128B-swizzled 64-wide
 // halves of head_dim).  TWO CTAs are resident per SM (112 KiB shared memory, 256 TMEM columns each) and hide each other's
 // softmax / MMA / barrier latencies.
-//   warp 0 / lane 0 : TMA producer (Q once; 2-deep rings of K and V pages; page ids from the block table)
-//   warp 1 / lane 0 : MMA issuer    S_j = Q K_j^T   (128 x 64 x 128: 8 k-steps over the two head_dim halves, SS) -> TMEM S
+//   warp 5 / lane 0 : TMA producer (Q once; 2-deep rings of K and V pages; page ids from the block table)
+//   warp 4 / lane 0 : MMA issuer    S_j = Q K_j^T   (128 x 64 x 128: 8 k-steps over the two head_dim halves, SS) -> TMEM S
 //                                    O  += P_j V_j   (two 128 x 64 x 64 MMAs, one per head_dim half; V is the MN-major B
 //                                                     operand exactly as TMA delivers a page)                    -> TMEM O
-//   warps 2..5      : softmax, one thread per query row: the 64 scores of a block are read from TMEM once, masked
+//   warps 0..3      : softmax, one thread per query row: the 64 scores of a block are read from TMEM once, masked
 //                     causally (only the diagonal blocks need it), exponentiated (exp2, log2e folded into the scale) and
 //                     parked as fp16 in a swizzled smem tile = the A operand of the PV MMA.  O stays in TMEM and is only
 //                     rescaled when the running row max grew by more than 2^8 (lazy rescale).
@@ -31,7 +31,10 @@ constexpr int kDh = 128;
 constexpr int kSub = 64;   // head_dim elements per 128-byte swizzled row
 constexpr int kQSub = kQ * kSub * 2;   // 16 KiB: [128 rows][64 dh]
 constexpr int kKVSub = kKB * kSub * 2; // 8 KiB:  [64 keys][64 dh]
-constexpr int kThreads = 192;          // TMA warp + MMA warp + 4 softmax warps
+constexpr int kThreads = 192;          // 4 softmax warps + MMA warp + TMA warp
+// the warp scheduler prefers the highest ready warp id: the single-thread MMA issuer / TMA producer sit ABOVE the softmax
+// warps (as warp 1 the issuer of the ViT kernel started a PV MMA thousands of cycles after its operands were ready)
+constexpr int kMmaWarp = 4, kTmaWarp = 5;
 // smem: Q (2 halves) | K ring [2][2 halves] | V ring [2][2 halves] | P [128][64 keys] | barriers
 constexpr int kOffK = 2 * kQSub, kOffV = kOffK + 4 * kKVSub, kOffP = kOffV + 4 * kKVSub, kOffBar = kOffP + kQ * kKB * 2;
 constexpr int kSmemBytes = kOffBar + 768;  // 115,456 B: two CTAs per SM
@@ -80,7 +83,7 @@ attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     for (int i = 0; i < kNumBars; ++i) mbar_init(bar(i), (i == kBarP || i == kBarSFree) ? 4 : 1);
     fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), kTmemCols);
     tmem_relinquish();
   }
@@ -89,7 +92,7 @@ attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == kTmaWarp) {
     if (lane == 0) {
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmK);
@@ -112,7 +115,7 @@ attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         tma_load_3d(sV + slot * 2 * kKVSub + kKVSub, &tmV, bar(kBarVFull + slot), kSub, 0, pg);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_f16(kQ, kKB);       // 128 x 64, both operands K-major
       constexpr uint32_t idesc_o = make_idesc_f16_bmn(kQ, kSub);  // 128 x 64, B (= V half) MN-major
@@ -213,7 +216,7 @@ attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         mbar_wait(bar(kBarVFull + (j & 1)), (j >> 1) & 1);
         uint8_t* vb = smem + kOffV + (j & 1) * 2 * kKVSub;
         for (int hf = 0; hf < 2; ++hf)
-          for (int off = nkeys_blk * 128 + (static_cast<int>(threadIdx.x) - 64) * 16; off < kKVSub; off += 128 * 16)
+          for (int off = nkeys_blk * 128 + static_cast<int>(threadIdx.x) * 16; off < kKVSub; off += 128 * 16)
             *reinterpret_cast<uint4*>(vb + hf * kKVSub + off) = make_uint4(0, 0, 0, 0);
       }
 
@@ -308,7 +311,7 @@ attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem, kTmemCols);

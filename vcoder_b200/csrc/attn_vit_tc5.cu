@@ -14,6 +14,8 @@
 // frees the S buffer for the next QK^T immediately), the two half-row maxima are exchanged through smem, and O stays in
 // TMEM across key blocks — it is only touched by the CUDA cores when the running max grows by more than 2^8 (lazy
 // rescale, as in FlashAttention-4), and once at the end for the 1/l normalisation.
+// Built only with VCB_EXPERIMENTAL=1 (python -m vcoder_b200.build): superseded by the pair schedule of attn_vit_pair.cu.
+#ifdef VCB_EXPERIMENTAL
 #include <cstdio>
 #include <cstdlib>
 
@@ -361,3 +363,11 @@ int attn_vit_tc5(const AttnPrefillParams& a, cudaStream_t stream) {
 }
 
 }  // namespace vcb
+
+#else  // !VCB_EXPERIMENTAL
+#include "common.h"
+#include "kernels.h"
+namespace vcb {
+int attn_vit_tc5(const AttnPrefillParams& p, cudaStream_t stream) { return attn_vit_pair(p, stream); }
+}  // namespace vcb
+#endif

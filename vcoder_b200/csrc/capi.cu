@@ -23,7 +23,11 @@ static int require_device() {
 
 extern "C" {
 
-const char* vcb_version(void) { return "vcoder_b200 0.1.0 (sm_100a)"; }
+#ifdef VCB_EXPERIMENTAL
+const char* vcb_version(void) { return "vcoder_b200 0.2.0 (sm_100a, experimental variants)"; }
+#else
+const char* vcb_version(void) { return "vcoder_b200 0.2.0 (sm_100a)"; }
+#endif
 const char* vcb_last_error(void) { return get_thread_error(); }
 
 int vcb_device_count(void) {

@@ -70,6 +70,26 @@ __global__ void ex2_bench_kernel(int iters, int with_fma, unsigned long long* cy
   if (s == 123.456f) sink[0] = s;
 }
 
+// packed-half MUFU: ex2.approx.ftz.f16x2 — two exponentials per instruction; is it twice the rate?
+__global__ void ex2_h2_bench_kernel(int iters, unsigned long long* cycles, float* sink) {
+  uint32_t x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = 0xB000B400u + threadIdx.x + i;  // small negative halves
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(x[i]));
+  }
+  __syncthreads();
+  const long long t1 = clock64();
+  if (threadIdx.x == 0) cycles[blockIdx.x] = static_cast<unsigned long long>(t1 - t0);
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s ^= x[i];
+  if (s == 0x12345678u) sink[0] = 1.f;
+}
+
 }  // namespace
 
 // which = 0: TMEM read, returns bytes per clock per SM; which = 1: ex2 (param = with_fma), returns ex2 per clock per SM
@@ -85,8 +105,10 @@ int microbench(int which, int warps, int param, int iters, float* result) {
       if (param <= 1) tmem_read_bench_kernel<1><<<n_sm, warps * 32>>>(iters, cyc, static_cast<uint32_t*>(sink));
       else if (param == 2) tmem_read_bench_kernel<2><<<n_sm, warps * 32>>>(iters, cyc, static_cast<uint32_t*>(sink));
       else tmem_read_bench_kernel<4><<<n_sm, warps * 32>>>(iters, cyc, static_cast<uint32_t*>(sink));
-    } else {
+    } else if (which == 1) {
       ex2_bench_kernel<<<n_sm, warps * 32>>>(iters, param, cyc, static_cast<float*>(sink));
+    } else {
+      ex2_h2_bench_kernel<<<n_sm, warps * 32>>>(iters, cyc, static_cast<float*>(sink));
     }
   }
   cudaError_t e = cudaDeviceSynchronize();
@@ -100,8 +122,10 @@ int microbench(int which, int warps, int param, int iters, float* result) {
   if (which == 0) {
     const int ilp = param <= 1 ? 1 : param == 2 ? 2 : 4;
     *result = static_cast<float>(static_cast<double>(warps) * iters * ilp * 4096.0 / avg);
-  } else {
+  } else if (which == 1) {
     *result = static_cast<float>(static_cast<double>(warps) * 32 * iters * 8.0 / avg);
+  } else {
+    *result = static_cast<float>(static_cast<double>(warps) * 32 * iters * 16.0 / avg);  // two exponentials per instruction
   }
   return kOk;
 }

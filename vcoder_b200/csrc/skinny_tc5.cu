@@ -10,6 +10,8 @@
 // K is split across the CTAs of a thread-block cluster (<= 8); the partial accumulators are reduced through
 // distributed shared memory in rank order (deterministic), and rank 0 applies the epilogue (SwiGLU / residual) and stores.
 // Programmatic dependent launch: the W tiles of the first ring fill are requested BEFORE griddepcontrol.wait.
+// Built only with VCB_EXPERIMENTAL=1 (python -m vcoder_b200.build): measured slower than the TMA-fed kernels.
+#ifdef VCB_EXPERIMENTAL
 #include <cstdlib>
 
 #include "common.h"
@@ -235,3 +237,15 @@ int skinny_gemm_tc5(const SkinnyParams& p, cudaStream_t stream) {
 }
 
 }  // namespace vcb
+
+#else  // !VCB_EXPERIMENTAL
+#include "common.h"
+#include "kernels.h"
+namespace vcb {
+bool skinny_tc5_supported(const SkinnyParams&) { return false; }
+int skinny_gemm_tc5(const SkinnyParams&, cudaStream_t) {
+  set_thread_error("skinny_gemm_tc5: built without VCB_EXPERIMENTAL");
+  return kErrInvalid;
+}
+}  // namespace vcb
+#endif

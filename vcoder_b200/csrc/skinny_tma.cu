@@ -332,11 +332,17 @@ int launch_tma(const CUtensorMap& tm, const SkinnyParams& p, int grid, cudaStrea
 // packed weight stream: the measured-best ring shape (4 warps x 2 stages x 8 KiB), or 3 stages (VCB_SKINNY_TMA_DEPTH=3)
 template <int NB>
 int launch_packed(const SkinnyParams& p, int grid, int depth, cudaStream_t stream) {
+#ifdef VCB_EXPERIMENTAL
   CUtensorMap unused;
   memset(&unused, 0, sizeof(unused));
   if (p.pn_parts != nullptr || p.cn_rstd != nullptr) return launch_tma<NB, 4, 2, 4, true, true>(unused, p, grid, stream);
   if (depth >= 3) return launch_tma<NB, 4, 3, 4, true>(unused, p, grid, stream);
   return launch_tma<NB, 4, 2, 4, true>(unused, p, grid, stream);
+#else
+  (void)p; (void)grid; (void)depth; (void)stream;
+  set_thread_error("the tile-major packed weight stream is an experiment (no gain measured): rebuild with VCB_EXPERIMENTAL=1");
+  return kErrInvalid;
+#endif
 }
 
 // row-major W[N,K] -> tile-major, pre-swizzled copy (one thread per 16-byte chunk): chunk c of row n goes to
@@ -356,6 +362,7 @@ int launch_tma_w(const CUtensorMap& tm, const SkinnyParams& p, int grid, int war
                  cudaStream_t stream) {
   // the chained RMSNorm (opt-in experiment) exists for the default ring shape only
   if (p.pn_parts != nullptr || p.cn_rstd != nullptr) return launch_tma<NB, 4, 2, 4, false, true>(tm, p, grid, stream);
+#ifdef VCB_EXPERIMENTAL  // ring-shape sweep (tools/sweep_decode.py; no shape beat 4 warps x 2 stages x 8 KiB: DESIGN.md 3.1)
   if (group == 2) {
     if (depth <= 2) return launch_tma<NB, 4, 2, 2>(tm, p, grid, stream);
     if (depth == 3) return launch_tma<NB, 4, 3, 2>(tm, p, grid, stream);
@@ -372,6 +379,10 @@ int launch_tma_w(const CUtensorMap& tm, const SkinnyParams& p, int grid, int war
   }
   if (depth <= 2) return launch_tma<NB, 2, 2, 4>(tm, p, grid, stream);
   return launch_tma<NB, 2, 3, 4>(tm, p, grid, stream);
+#else
+  (void)warps; (void)depth; (void)group;
+  return launch_tma<NB, 4, 2, 4>(tm, p, grid, stream);
+#endif
 }
 
 }  // namespace
