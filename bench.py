@@ -342,6 +342,13 @@ METRIC = "end-to-end tokens/sec (prefill+decode) VCoder-DS-7B bs8"
 
 
 def workload_config(args, world):
+    if getattr(args, "variant", "ds") == "vcoder":
+        which = ("BASELINE.json configs[1]" if (args.preset, args.batch, args.new_tokens) == ("7b", 1, 32) else "non-headline shape")
+        return {"workload": f"VCoder LLaVA-1.5-{args.preset.upper()}, RGB+seg towers (CLIP ViT-L/14@336), batch {args.batch} per GPU, "
+                            f"prompt 57 ids -> T'=1207 spliced tokens, {args.new_tokens} new tokens, greedy ({which})",
+                "global_batch": args.batch * world, "new_tokens": args.new_tokens, "parallelism": f"dp{world} (replicas, one NCCL all-gather of ids)",
+                "l2": "inputs larger than L2: 13.5 GB of weights streamed per decode step vs 126 MB L2; no explicit flush",
+                "weights": "seeded random-init fp16 (HF std 0.02)"}
     which = ("BASELINE.json configs[2]" if (args.preset, args.batch, args.new_tokens) == ("7b", 8, 128)
              else "BASELINE.json configs[3], one GPU's slice of the batch-32 job" if (args.preset, args.batch, args.new_tokens) == ("13b", 4, 256)
              else "non-headline shape")
@@ -382,16 +389,20 @@ def run_b200(args):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
-    g = synth.PRESETS[args.preset].with_variant(synth.VARIANT_VCODER_DS)
+    ds = args.variant == "ds"
+    g = synth.PRESETS[args.preset].with_variant(synth.VARIANT_VCODER_DS if ds else synth.VARIANT_VCODER)
     B, N = args.batch, args.new_tokens
-    ids = synth.make_prompt_ids(g, B, seed=rank)  # [B, 58]
-    Tp = ids.shape[1] - 3 + 2 * g.n_patches
+    ids = synth.make_prompt_ids(g, B, seed=rank)  # [B, 58] (DS: IMAGE, DEPTH, SEG) / [B, 57] (VCoder: IMAGE, SEG)
+    n_spec = 3 if ds else 2
+    Tp = ids.shape[1] - n_spec + 2 * g.n_patches
     eng = Engine(g, max_batch=B, max_seq_len=((Tp + N + 63) // 64) * 64, device=local)
     bind_synthetic(eng, g, seed=0, device=dev)
     torch.cuda.synchronize()
     host_px = [synth.make_pixels(g, B, 10 * rank + s).pin_memory() for s in (1, 2, 3)]
+    if not ds:
+        host_px[2] = None  # VCoder (BASELINE configs[1]): RGB + seg towers only
     ids_pinned = ids.pin_memory()
-    dev_px = [p.to(dev) for p in host_px]
+    dev_px = [p.to(dev) if p is not None else None for p in host_px]
     gathered = torch.empty(world * B, N, dtype=torch.int32, device=dev) if world > 1 else None
     stream = torch.cuda.current_stream()
 
@@ -487,10 +498,12 @@ def run_b200(args):
         bytes_per_launch = step_bytes * rounds / max(1, n_ws.value)
         ach = bytes_per_launch / (avg_launch_us * 1e-6) / 1e9 if avg_launch_us else None
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "skinny_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "r02_skinny_traffic.json")
+        if not os.path.exists(tp):
+            tp = os.path.join(ROOT, "profiles", "skinny_traffic.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        roofline = {"kernel": "skinny_tma_kernel (TMA-fed decode weight streaming: qkv/o/gate-up/down/lm_head)", "bound": "hbm",
+        roofline = {"kernel": "skinny_stream_kernel (TMA-fed decode weight streaming, balanced multi-tile CTAs: qkv/o/gate-up/down/lm_head)", "bound": "hbm",
                     "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": (ach / peaks["hbm_gbs"]) if ach else None,
                     "traffic": traffic, "peak_source": peaks["source"],
                     "bytes_per_launch_avg": bytes_per_launch, "avg_launch_us": avg_launch_us, "launches": n_ws.value,
@@ -500,12 +513,13 @@ def run_b200(args):
                     "note": "achieved_with_per_launch_events = same bytes / sum of per-launch event pairs inside one full "
                             "job (graph off, ~2 us event overhead per launch, no PDL overlap): a lower bound"}
         # secondary: the kernel the north star names (CLIP self-attention) and the three-tower throughput
-        n_img_layers = 3 * B * (g.vit_layers - 1)
+        n_kinds = 3 if ds else 2
+        n_img_layers = n_kinds * B * (g.vit_layers - 1)
         av = breakdown["attn_vit"]
         attn_us = av["ms"] * 1e3 / n_img_layers if av["ms"] else None
         attn_bytes = 4 * (g.n_patches + 1) * g.vit_hidden * 2
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        px_all = torch.cat(dev_px, dim=0)
+        px_all = torch.cat([p for p in dev_px if p is not None], dim=0)
         eng.tower_forward(px_all)
         ev[0].record(stream)
         for _ in range(3):
@@ -513,8 +527,8 @@ def run_b200(args):
         ev[1].record(stream)
         torch.cuda.synchronize()
         tower_ms = ev[0].elapsed_time(ev[1]) / 3
-        vit = {"images": 3 * B, "tower_ms": round(tower_ms, 3), "images_per_s": round(3 * B / (tower_ms / 1e3), 1),
-               "tower_tflops": round(3 * B * 366e9 / (tower_ms / 1e3) / 1e12, 1),
+        vit = {"images": n_kinds * B, "tower_ms": round(tower_ms, 3), "images_per_s": round(n_kinds * B / (tower_ms / 1e3), 1),
+               "tower_tflops": round(n_kinds * B * 366e9 / (tower_ms / 1e3) / 1e12, 1),
                "attn_us_per_image_layer": round(attn_us, 3) if attn_us else None,
                "attn_hbm_frac": round(attn_bytes / (attn_us * 1e-6) / 1e9 / peaks["hbm_gbs"], 4) if attn_us else None,
                "attn_tflops": round(4 * (g.n_patches + 1) ** 2 * g.vit_hidden / (attn_us * 1e-6) / 1e12, 1) if attn_us else None,
@@ -553,14 +567,14 @@ def run_b200(args):
         try:
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import bench_hf_library as hfl
-            library = hfl.measure(g, dev, B, N, reps=2, engine_ids=g_ids.long() if ids_check else None)
+            library = hfl.measure(g, dev, B, N, reps=2, engine_ids=g_ids.long() if ids_check else None, ds=ds)
         except Exception as ex:  # a reported baseline must never take the bench line down
             library = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
     if rank == 0:
-        h2d = sum(p.numel() * 2 for p in host_px) + ids.numel() * 8
-        headline = (args.preset, args.batch) == ("7b", 8)
+        h2d = sum(p.numel() * 2 for p in host_px if p is not None) + ids.numel() * 8
+        headline = (args.preset, args.batch, args.variant) == ("7b", 8, "ds")
         line = {
-            "metric": METRIC if headline else f"end-to-end tokens/sec (prefill+decode) VCoder-DS-{args.preset.upper()} bs{args.batch}",
+            "metric": METRIC if headline else f"end-to-end tokens/sec (prefill+decode) VCoder{'-DS' if ds else ''}-{args.preset.upper()} bs{args.batch}",
             "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f16", "data": "synthetic", "config": workload_config(args, world),
@@ -585,6 +599,8 @@ def main():
     ap.add_argument("--preset", default="7b")
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--new-tokens", type=int, default=128)
+    ap.add_argument("--variant", default="ds", choices=["ds", "vcoder"],
+                    help="ds: VCoder-DS (RGB+seg+depth, the headline); vcoder: VCoder (RGB+seg; BASELINE configs[1] with --batch 1 --new-tokens 32)")
     ap.add_argument("--global-batch", type=int, default=0,
                     help="strong scaling: fixed global batch split over the ranks (overrides --batch; reported as scaling=strong)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -110,6 +110,13 @@ int vcb_op_skinny_gemm_f16(const vcb_half* X_dev, int32_t ldx, const vcb_half* W
                            const vcb_half* residual_dev, int32_t ldr, int32_t swiglu, vcb_half* Y_dev, int32_t ldy,
                            void* stream);
 
+/* The same GEMM through the round-1 kernel (one CTA per 16-row tile of W; needs K % 64 == 0).  vcb_op_skinny_gemm_f16 runs the
+ * balanced multi-tile kernel (every CTA streams ceil(tiles / resident CTAs) consecutive tiles): identical arithmetic in
+ * identical order, so the two must agree bit for bit — that is what this entry exists to test. */
+int vcb_op_skinny_gemm_onetile_f16(const vcb_half* X_dev, int32_t ldx, const vcb_half* W_dev, int32_t B, int32_t N, int32_t K,
+                                   const vcb_half* residual_dev, int32_t ldr, int32_t swiglu, vcb_half* Y_dev, int32_t ldy,
+                                   void* stream);
+
 /* The decode weight stream's own HBM layout.  vcb_op_pack_skinny_weights copies a row-major W[N,K] (N % 16 == 0,
  * K % 64 == 0) into the tile-major form [N/16][K/64][16 rows][128 B] (16-byte chunks pre-swizzled with row & 7), i.e. the
  * shared-memory image of every 16-row x 64-k block, so that a CTA's 16 x K slab is one contiguous run and a pipeline stage

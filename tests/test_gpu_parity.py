@@ -323,6 +323,32 @@ def test_llama_real_width(name, hidden, heads, ffn, layers, batch):
 # ---------------------------------------------------------------------------------------------------------------
 # decode weight stream from the tile-major (packed) weight copy: same arithmetic in the same order => bit-identical
 # ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,N,K,sw,res", [(8, 12288, 4096, 0, 0), (8, 22016, 4096, 1, 0), (8, 4096, 11008, 0, 1), (8, 32000, 4096, 0, 0),
+                                          (4, 27648, 5120, 1, 0), (1, 32000, 4096, 0, 0), (16, 22016, 4096, 1, 0), (3, 512, 256, 0, 1),
+                                          (32, 7168, 512, 0, 1), (8, 7120, 192, 0, 0)])
+def test_skinny_gemm_multi_tile_bit_identical_to_one_tile_per_cta(B, N, K, sw, res):
+    """The balanced multi-tile kernel (default) must reproduce the one-CTA-per-tile kernel bit for bit at the decode shapes
+    of 7B / 13B (several tiles per CTA, ragged last CTA) and at small shapes (one tile per CTA, fewer k-groups than warps)."""
+    lib = _lib.load()
+    torch.manual_seed(B + N + K)
+    X = (torch.randn(B, K, device=DEV) * 0.5).half()
+    W = (torch.randn(N, K, device=DEV) * 0.03).half()
+    R = torch.randn(B, N, device=DEV).half() if res else None
+    No = N // 2 if sw else N
+    Y0 = torch.full((B, No), float("nan"), device=DEV, dtype=torch.float16)
+    Y1 = torch.full((B, No), float("nan"), device=DEV, dtype=torch.float16)
+    _lib.check(lib.vcb_op_skinny_gemm_onetile_f16(_lib.ptr(X), K, _lib.ptr(W), B, N, K, _lib.ptr(R), N, sw, _lib.ptr(Y0), No, ST))
+    _lib.check(lib.vcb_op_skinny_gemm_f16(_lib.ptr(X), K, _lib.ptr(W), B, N, K, _lib.ptr(R), N, sw, _lib.ptr(Y1), No, ST))
+    torch.cuda.synchronize()
+    assert not torch.isnan(Y1.float()).any()
+    assert torch.equal(Y0.view(torch.int16), Y1.view(torch.int16)), max_abs(Y0, Y1)
+
+
+def _experimental_build():
+    """The rejected A/B variants are only compiled with VCB_EXPERIMENTAL=1 (python -m vcoder_b200.build)."""
+    return b"experimental" in _lib.load().vcb_version()
+
+
 def _pack_numpy(W):
     """[N,K] -> [N/16][K/64][16][8 chunks of 8 halves], chunk position = ch ^ (r & 7) (include/vcoder_b200.h)."""
     N, K = W.shape
@@ -338,6 +364,8 @@ def _pack_numpy(W):
                                           (1, 32000, 4096, 0, 0), (16, 2048, 1024, 0, 1), (32, 1024, 512, 1, 0),
                                           (8, 4096, 11008, 0, 1), (8, 64, 64, 0, 0)])
 def test_skinny_gemm_packed_bit_identical(B, N, K, sw, res):
+    if not _experimental_build():
+        pytest.skip("packed weight stream: experimental variant, not in the default build")
     lib = _lib.load()
     torch.manual_seed(B + N + K)
     X = (torch.randn(B, K, device=DEV) * 0.5).half()
@@ -360,6 +388,8 @@ def test_skinny_gemm_packed_bit_identical(B, N, K, sw, res):
 def test_engine_with_packed_weight_stream_matches_row_major(monkeypatch):
     """VCB_SKINNY_PACKED=1: the handle keeps a tile-major copy of every matrix the decode step streams; ids and logits must
     equal the row-major engine's bit for bit (and therefore the oracle's / the reference fixtures' as tested above)."""
+    if not _experimental_build():
+        pytest.skip("packed weight stream: experimental variant, not in the default build")
     g = synth.PRESETS["tiny"].with_variant(synth.VARIANT_VCODER_DS)
     sd = synth.make_state_dict(g, seed=0)
     ids = synth.make_prompt_ids(g, 2, seed=4, n_before=6, n_after=5)

@@ -83,18 +83,21 @@ def encode(tower, proj, which, pixels, select_layer=-2):
 
 
 @torch.no_grad()
-def generate(g, tower, llm, proj, ids, images, segs, depths, n_new, keep_trace=True):
+def generate(g, tower, llm, proj, ids, images, segs, depths, n_new, keep_trace=True, ds=True):
     """-> (new ids [B, n_new] on the host, per-step logits list or None).  keep_trace=False: no per-step host copy."""
     from vcoder_b200 import synth
     from vcoder_b200.engine import splice_plan
     B = ids.shape[0]
-    feats = [encode(tower, proj, "image", images), encode(tower, proj, "seg", segs), encode(tower, proj, "depth", depths)]
+    feats = [encode(tower, proj, "image", images), encode(tower, proj, "seg", segs)]
+    if ds:
+        feats.append(encode(tower, proj, "depth", depths))
     P = g.n_patches
-    plan = torch.from_numpy(splice_plan(synth.VARIANT_VCODER_DS, ids.cpu().numpy(), P, True, [True] * B)).to(ids.device).long()
+    variant = synth.VARIANT_VCODER_DS if ds else synth.VARIANT_VCODER
+    plan = torch.from_numpy(splice_plan(variant, ids.cpu().numpy(), P, True, [True] * B if ds else None)).to(ids.device).long()
     # feature buffer in the planner's row order: [kind][B][1 + P] (row 0 of every image = CLS, never referenced)
     H = feats[0].shape[-1]
     fbuf = torch.zeros(3, B, P + 1, H, dtype=feats[0].dtype, device=feats[0].device)
-    for k in range(3):
+    for k in range(len(feats)):
         fbuf[k, :, 1:] = feats[k]
     fbuf = fbuf.view(-1, H)
     emb = llm.model.embed_tokens.weight
@@ -113,19 +116,19 @@ def generate(g, tower, llm, proj, ids, images, segs, depths, n_new, keep_trace=T
     return torch.stack(new, dim=1).cpu(), trace
 
 
-def measure(g, dev, B, N, reps=2, engine_ids=None, seed=0):
+def measure(g, dev, B, N, reps=2, engine_ids=None, seed=0, ds=True):
     """bench.py's `library_baseline`: the job through the HF library modules in fp16 on `dev` (1 warm-up + `reps` timed
     runs, wall clock with synchronize on both sides), and where its greedy ids first differ from `engine_ids` [B, N]."""
     from vcoder_b200 import synth
     tower, llm, proj = build_modules(g, str(dev), torch.float16, seed=seed)
     ids = synth.make_prompt_ids(g, B, seed=0).to(dev)
     px = [synth.make_pixels(g, B, s).to(dev, torch.float16) for s in (1, 2, 3)]
-    new, trace = generate(g, tower, llm, proj, ids, *px, N)  # warm-up; its logits serve the token comparison
+    new, trace = generate(g, tower, llm, proj, ids, *px, N, ds=ds)  # warm-up; its logits serve the token comparison
     times = []
     for r in range(reps):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        new2, _ = generate(g, tower, llm, proj, ids, *px, N, keep_trace=False)
+        new2, _ = generate(g, tower, llm, proj, ids, *px, N, keep_trace=False, ds=ds)
         torch.cuda.synchronize()
         times.append(time.perf_counter() - t0)
     times.sort()

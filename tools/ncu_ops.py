@@ -44,4 +44,26 @@ if which in ("all", "gemm"):
         for _ in range(2):
             lib.vcb_op_gemm_f16(_lib.ptr(A), K, _lib.ptr(W), K, M, N, K, None, None, N, act, _lib.ptr(Cc), No, 0, st)
         torch.cuda.synchronize()
+if which in ("all", "attn_llama"):
+    # LLaMA attention at the benched shape: prefill B = 8, T' = 1207 (tcgen05 kernel); decode B = 8, ctx = 1271 (streaming kernel)
+    import math
+    B, heads, T = 8, 32, 1207
+    H = heads * 128
+    max_pages = (T + 128 + 63) // 64
+    n_pages = B * max_pages
+    k_pool = torch.randn(n_pages, heads, 64, 128, device=dev).half()
+    v_pool = torch.randn(n_pages, heads, 64, 128, device=dev).half()
+    bt = torch.arange(n_pages, device=dev, dtype=torch.int32).view(B, max_pages).contiguous()
+    q = torch.randn(B * T, 3 * H, device=dev).half()
+    out = torch.empty(B * T, H, device=dev, dtype=torch.float16)
+    for _ in range(2):
+        _lib.check(lib.vcb_op_attention_prefill_f16(_lib.ptr(q), 3 * H, _lib.ptr(k_pool), _lib.ptr(v_pool), _lib.ptr(bt), max_pages, B, heads,
+                                                    T, 0, 1.0 / math.sqrt(128), _lib.ptr(out), H, st))
+    qkv = torch.randn(B, 3 * H, device=dev).half()
+    od = torch.empty(B, H, device=dev, dtype=torch.float16)
+    for _ in range(3):
+        flush.zero_()
+        _lib.check(lib.vcb_op_attention_decode_f16(_lib.ptr(qkv), _lib.ptr(k_pool), _lib.ptr(v_pool), _lib.ptr(bt), max_pages, B, heads, 1271, 1335,
+                                                   1, 10000.0, 1.0 / math.sqrt(128), _lib.ptr(od), st))
+    torch.cuda.synchronize()
 print("done")

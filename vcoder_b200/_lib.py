@@ -54,6 +54,7 @@ SIGNATURES = {
     "vcb_device_count": (C.c_int, []),
     "vcb_op_gemm_f16": (C.c_int, [_p, _i32, _p, _i32, _i32, _i32, _i32, _p, _p, _i32, _i32, _p, _i32, _i32, _p]),
     "vcb_op_skinny_gemm_f16": (C.c_int, [_p, _i32, _p, _i32, _i32, _i32, _p, _i32, _i32, _p, _i32, _p]),
+    "vcb_op_skinny_gemm_onetile_f16": (C.c_int, [_p, _i32, _p, _i32, _i32, _i32, _p, _i32, _i32, _p, _i32, _p]),
     "vcb_op_pack_skinny_weights": (C.c_int, [_p, _i32, _i32, _p, _p]),
     "vcb_op_skinny_gemm_packed_f16": (C.c_int, [_p, _i32, _p, _i32, _i32, _i32, _p, _i32, _i32, _p, _i32, _p]),
     "vcb_op_skinny_rmsnorm_gemm_f16": (C.c_int, [_p, _i32, _p, _f, _p, _i32, _i32, _i32, _p, _i32, _i32, _p, _i32, _p]),

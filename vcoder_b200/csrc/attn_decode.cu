@@ -468,7 +468,8 @@ attn_decode_tma_kernel(AttnDecodeParams p, int splits) {
 }  // namespace
 
 namespace {
-// VCB_ATTN_DEC: default = register-staged split kernel + combine kernel.  "merge": the same split kernel whose last CTA per
+// VCB_ATTN_DEC: default "stream" = the balanced page-streaming kernel of attn_decode_stream.cu (+ its combine kernel).
+// "split": the register-staged split kernel of this file + combine kernel (round 1).  "merge": the same split kernel whose last CTA per
 // (sequence, head) merges the partials (threadfence + ticket): measured SLOWER (38.9 vs 33.3 + 2.4 + 0.6 us per layer at
 // B = 8, ctx 1271; profiles/r02_trace_decode_merge_last_cta.csv) — the fence + atomic tail of 1536 CTAs costs more than one
 // small launch.  "tma": the bulk-copy fed kernel, also slower (46 us: a CTA loads its 64 KiB, computes and leaves, so its
@@ -477,7 +478,7 @@ int decode_attn_impl() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("VCB_ATTN_DEC");
-    v = (e == nullptr) ? 1 : (e[0] == 't' ? 2 : (e[0] == 'm' ? 0 : 1));
+    v = (e == nullptr) ? 3 : (e[0] == 't' ? 2 : (e[0] == 'm' ? 0 : (e[0] == 's' && e[1] == 'p' ? 1 : 3)));
   }
   return v;
 }
@@ -513,6 +514,7 @@ int attn_llama_decode(const AttnDecodeParams& p_in, cudaStream_t stream) {
   if (env_pf < 0) { const char* e = getenv("VCB_ATTN_DEC_PF"); env_pf = e ? atoi(e) : 1; }  // measured: DESIGN.md section 3.1
   p.prefetch = env_pf;
   p.chunk = decode_attn_chunk();
+  if (decode_attn_impl() == 3) return attn_llama_decode_stream(p_in, stream);
   const int splits = attn_decode_splits(p.max_ctx);
   VCB_CHECK(splits >= 1, kErrInvalid, "attn_llama_decode: empty context");
   VCB_CHECK(p.page_tokens == kPT, kErrInvalid, "attn_llama_decode: KV page must hold 64 tokens");

@@ -85,6 +85,16 @@ int vcb_op_skinny_gemm_f16(const vcb_half* X, int32_t ldx, const vcb_half* W, in
   return skinny_gemm(s, ST(stream));
 }
 
+int vcb_op_skinny_gemm_onetile_f16(const vcb_half* X, int32_t ldx, const vcb_half* W, int32_t B, int32_t N, int32_t K,
+                                   const vcb_half* residual, int32_t ldr, int32_t swiglu, vcb_half* Y, int32_t ldy,
+                                   void* stream) {
+  VCB_TRY(require_device());
+  SkinnyParams s;
+  s.X = H(X); s.ldx = ldx; s.W = H(W); s.Y = H(Y); s.ldy = ldy; s.residual = H(residual); s.ldr = ldr;
+  s.B = B; s.N = N; s.K = K; s.swiglu = swiglu;
+  return skinny_gemm_tma(s, ST(stream));
+}
+
 int vcb_op_pack_skinny_weights(const vcb_half* W, int32_t N, int32_t K, vcb_half* Wp, void* stream) {
   VCB_TRY(require_device());
   return pack_skinny_weights(H(W), H(Wp), N, K, ST(stream));
@@ -161,7 +171,7 @@ int vcb_op_attention_decode_f16(const vcb_half* qkv, vcb_half* k_pool, vcb_half*
   VCB_CHECK(B >= 1 && heads >= 1 && ctx_len >= 1 && max_ctx >= ctx_len && (max_ctx + 63) / 64 <= max_pages, kErrInvalid,
             "vcb_op_attention_decode_f16: bad shape");
   cudaStream_t st = ST(stream);
-  const int splits = attn_decode_splits(max_ctx);
+  const int splits = std::max(attn_decode_splits(max_ctx), attn_decode_stream_slots(B, heads));
   const size_t n_po = static_cast<size_t>(B) * heads * splits * 128 * 4, n_pml = static_cast<size_t>(B) * heads * splits * 2 * 4;
   const size_t n_cs = fuse_rope ? static_cast<size_t>(ctx_len) * 64 * sizeof(float2) : 0;
   const size_t n_sync = (static_cast<size_t>(B) * heads * 4 + 255) & ~static_cast<size_t>(255);

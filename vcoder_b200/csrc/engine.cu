@@ -172,8 +172,12 @@ int engine_create(const vcb_config* c, int device, Engine** out) {
   const int max_splits = attn_decode_splits(c->max_seq_len);
   if (rc == kOk) rc = dev_alloc(e, &e->next_ids, B * 4);
   if (rc == kOk) rc = dev_alloc(e, &e->trace, B * c->max_seq_len * 4);
-  if (rc == kOk) rc = dev_alloc(e, &e->part_o, B * c->llm_heads * max_splits * 128 * 4);
-  if (rc == kOk) rc = dev_alloc(e, &e->part_ml, B * c->llm_heads * max_splits * 2 * 4);
+  // flash-decoding partial states: [B*heads][splits] for the split kernel, [B*heads][slots(B)] for the page-streaming
+  // kernel (slots(B) = resident CTAs / (B*heads) + 2, so B*heads*slots(B) <= resident CTAs + 2*B*heads for every B)
+  const long part_entries = std::max<long>(B * c->llm_heads * max_splits,
+                                           static_cast<long>(attn_decode_stream_slots(1, c->llm_heads)) * c->llm_heads + 2L * B * c->llm_heads);
+  if (rc == kOk) rc = dev_alloc(e, &e->part_o, part_entries * 128 * 4);
+  if (rc == kOk) rc = dev_alloc(e, &e->part_ml, part_entries * 2 * 4);
   if (rc == kOk) rc = dev_alloc(e, &e->attn_sync, B * c->llm_heads * 4);
   if (rc == kOk) cudaMemset(e->attn_sync.p, 0, e->attn_sync.bytes);
   if (rc == kOk) rc = dev_alloc(e, &e->plan_dev, e->max_rows * 4);

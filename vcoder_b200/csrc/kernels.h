@@ -59,7 +59,9 @@ struct AttnDecodeParams {
   unsigned long long* trace = nullptr;   // timeline slots of the split kernel (common.h trace_slots), else null
   unsigned long long* trace2 = nullptr;  // ... of the combine kernel
 };
-int attn_llama_decode(const AttnDecodeParams& p, cudaStream_t stream);
+int attn_llama_decode(const AttnDecodeParams& p, cudaStream_t stream);         // dispatcher (VCB_ATTN_DEC=stream|split|...)
+int attn_llama_decode_stream(const AttnDecodeParams& p, cudaStream_t stream);  // balanced page-streaming kernel (attn_decode_stream.cu)
+int attn_decode_stream_slots(int batch, int n_heads);  // partial-state slots per (sequence, head) of the streaming kernel
 int attn_decode_splits(int max_ctx);
 
 // ---- skinny GEMM (decode / lm_head): Y[B,N] = X[B,K] * W[N,K]^T ---------------------------------------
