@@ -384,9 +384,13 @@ def run_b200(args):
         raise RuntimeError("bench.py --impl b200 needs a GPU: there is no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    real_stdout = None
     if world > 1:
-        # keep stdout to the ONE JSON line: NCCL's version / debug banner goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # keep stdout to the ONE JSON line: NCCL prints its version banner on fd 1 from native code (NCCL_DEBUG_FILE does not
+        # catch it), so fd 1 points at stderr for the whole run and the line is written to the saved descriptor at the end
+        sys.stdout.flush()
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     ds = args.variant == "ds"
@@ -585,7 +589,10 @@ def run_b200(args):
         }
         if ids_check:
             line.update(ids_check)
-        print(json.dumps(line), flush=True)
+        if real_stdout is not None:
+            os.write(real_stdout, (json.dumps(line) + "\n").encode())
+        else:
+            print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
