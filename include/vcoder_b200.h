@@ -187,6 +187,17 @@ int vcb_op_sample_f16(const vcb_half* logits_dev, int32_t B, int32_t V, float te
 int vcb_op_preprocess_u8(const uint8_t* img_any, int32_t height, int32_t width, const uint8_t* pad_rgb, int32_t out_size,
                          const float* mean3, const float* std3, vcb_half* out_dev, void* stream);
 
+/* bitsandbytes NF4 weight format as a load-time transform (reference: `load_pretrained_model(load_4bit=True)`,
+ * vcoder_llava/model/builder.py:28-37 -> BitsAndBytesConfig(nf4, double quant, compute dtype fp16)): out = the fp16 weights
+ * a bnb.nn.Linear4bit layer multiplies by, dequantize(quantize(w)).  n % 64 == 0 (blocks of 64 weights, absmax per block,
+ * nearest of the 16 NF4 levels); double_quant != 0: the absmax vector minus its mean goes through the 8-bit dynamic code in
+ * blocks of 256 (code8_host: the 256 sorted code values of create_dynamic_map, see vcoder_b200/nf4.py).  idx_out_dev
+ * (optional, n bytes) receives the 4-bit level indices.  w_dev may equal out_dev.  The 4-bit storage itself is not kept: the
+ * engine streams the de-quantised fp16 weights (same arithmetic, none of the memory saving).  PARITY UNPINNED: bitsandbytes
+ * is not available offline; the oracle restates the published algorithm (oracle/bnb_nf4_oracle.py). */
+int vcb_op_nf4_roundtrip_f16(const vcb_half* w_dev, int64_t n, int32_t double_quant, const float* code8_host, vcb_half* out_dev,
+                             uint8_t* idx_out_dev, void* stream);
+
 /* ---- host-only logic ------------------------------------------------------------------------ */
 
 /* The splice plan of prepare_inputs_labels_for_multimodal (vcoder_ds_llava_arch.py:175-312 /

@@ -73,12 +73,8 @@ def test_projector_only_checkpoint_with_model_base(tmp_path, monkeypatch):
 def test_rejected_layouts(tmp_path, monkeypatch):
     from vcoder_b200 import builder
     monkeypatch.setattr("vcoder_b200.model.Engine", RecordingEngine)
-    with pytest.raises(NotImplementedError):
-        builder.load_pretrained_model(str(tmp_path), None, "llava-tiny", load_4bit=True)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(NotImplementedError):  # LLM.int8 (builder.py:28-29) is not built
         builder.load_pretrained_model(str(tmp_path), None, "llava-tiny", load_8bit=True)
-    with pytest.raises(NotImplementedError):  # LoRA needs peft (builder.py:44-81)
-        builder.load_pretrained_model(str(tmp_path), str(tmp_path), "llava-tiny-lora", tokenizer="stub")
     with pytest.raises(ValueError):  # plain language models (builder.py:109-128) are not on the accelerated path
         builder.load_pretrained_model(str(tmp_path), None, "vicuna-7b", tokenizer="stub")
 
@@ -125,3 +121,69 @@ def test_generate_clamps_to_the_kv_capacity_and_validates_pixels(monkeypatch):
     assert eng_mod._as_half_any([good[0], good[1]]).shape == (2, 3, 56, 56)
     with pytest.raises(ValueError):
         eng_mod._as_half_any([good[0], torch.zeros(3, 28, 28)])
+
+
+def test_load_4bit_marks_the_model_for_nf4_binding(tmp_path, monkeypatch):
+    """builder.py:30-37: load_4bit=True -> BitsAndBytesConfig(nf4, double quant, fp16 compute).  Here: the model binds its
+    weights with nf4=True, and exactly the nn.Linear weights HF's quantizer would replace (all but lm_head; not the tower,
+    embeddings, norms or biases) are selected (vcoder_b200/nf4.py)."""
+    from vcoder_b200 import builder, nf4
+
+    class Eng(RecordingEngine):
+        def bind(self, sd, nf4=False):
+            self.nf4 = nf4
+            super().bind(sd)
+
+    monkeypatch.setattr("vcoder_b200.model.Engine", Eng)
+    g = synth.PRESETS["tiny"].with_variant(synth.VARIANT_VCODER_DS)
+    sd = synth.make_state_dict(g, seed=0)
+    vt = "model.vision_tower.vision_tower."
+    tower, model_dir = str(tmp_path / "tower"), str(tmp_path / "vcoder_ds_llava-tiny")
+    _save(tower, {k[len(vt):]: v for k, v in sd.items() if k.startswith(vt)})
+    _save(model_dir, {k: v for k, v in sd.items() if not k.startswith(vt)})
+    _configs(g, model_dir, tower)
+    _, model, *_ = builder.load_pretrained_model(model_dir, None, "vcoder_ds_llava-tiny", load_4bit=True, tokenizer="stub")
+    assert model.load_4bit and RecordingEngine.last.nf4 is True
+    _, model, *_ = builder.load_pretrained_model(model_dir, None, "vcoder_ds_llava-tiny", tokenizer="stub")
+    assert not model.load_4bit and RecordingEngine.last.nf4 is False
+    picked = sorted(k for k in sd if nf4.is_bnb_linear(k))
+    n_lin = g.llm_layers * 7 + 2 * sum(1 for k in sd if k.endswith("projector.0.weight"))
+    assert len(picked) == n_lin
+    assert not any(k.startswith(vt) or "lm_head" in k or "embed" in k or "norm" in k or k.endswith(".bias") for k in picked)
+
+
+def test_lora_checkpoint_is_merged_without_peft(tmp_path, monkeypatch):
+    """builder.py:44-81: `model_base` + a LoRA adapter under model_path -> base weights, non_lora_trainables on top, then
+    W += (B @ A) * alpha / r for every adapted Linear (what peft's merge_and_unload does), LlavaLlamaForCausalLM."""
+    from vcoder_b200 import builder
+
+    class Eng(RecordingEngine):
+        def bind(self, sd, nf4=False):
+            self.tensors = getattr(self, "tensors", {})
+            self.tensors.update({k: v.clone() for k, v in sd.items() if "layers.0.self_attn.q_proj" in k or "mm_projector.0.weight" in k})
+            super().bind(sd)
+
+    monkeypatch.setattr("vcoder_b200.model.Engine", Eng)
+    g = synth.PRESETS["tiny"].with_variant(synth.VARIANT_LLAVA)
+    sd = synth.make_state_dict(g, seed=0)
+    vt = "model.vision_tower.vision_tower."
+    tower, base, model_dir = (str(tmp_path / n) for n in ("tower", "vicuna-tiny", "llava-tiny-lora"))
+    _save(tower, {k[len(vt):]: v for k, v in sd.items() if k.startswith(vt)})
+    _save(base, {k: v for k, v in sd.items() if not k.startswith(vt) and "mm_projector" not in k})
+    _configs(g, model_dir, tower)
+    torch.save({"base_model.model." + k: v.float() for k, v in sd.items() if "mm_projector" in k},
+               os.path.join(model_dir, "non_lora_trainables.bin"))
+    r, alpha, H = 4, 8, g.llm_hidden
+    gen = torch.Generator().manual_seed(1)
+    A, B = torch.randn(r, H, generator=gen) * 0.05, torch.randn(H, r, generator=gen) * 0.05
+    json.dump({"peft_type": "LORA", "r": r, "lora_alpha": alpha, "target_modules": ["q_proj"], "fan_in_fan_out": False},
+              open(os.path.join(model_dir, "adapter_config.json"), "w"))
+    torch.save({"base_model.model.model.layers.0.self_attn.q_proj.lora_A.weight": A,
+                "base_model.model.model.layers.0.self_attn.q_proj.lora_B.weight": B}, os.path.join(model_dir, "adapter_model.bin"))
+    _, model, ip, sip, dip, _ = builder.load_pretrained_model(model_dir, base, "llava-tiny-lora", tokenizer="stub")
+    assert type(model).__name__ == "LlavaLlamaForCausalLM" and ip is not None and sip is None
+    got = RecordingEngine.last.tensors["model.layers.0.self_attn.q_proj.weight"]
+    w0 = sd["model.layers.0.self_attn.q_proj.weight"]
+    want = w0 + ((B.half() @ A.half()) * (alpha / r)).half()
+    assert torch.equal(got, want) and not torch.equal(got, w0)
+    assert torch.equal(RecordingEngine.last.tensors["model.mm_projector.0.weight"], sd["model.mm_projector.0.weight"])

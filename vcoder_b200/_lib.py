@@ -63,6 +63,7 @@ SIGNATURES = {
     "vcb_op_attention_vit_f16": (C.c_int, [_p, _i32, _i32, _i32, _f, _p, _p]),
     "vcb_op_attention_prefill_f16": (C.c_int, [_p, _i64, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _f, _p, _i64, _p]),
     "vcb_op_attention_decode_f16": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _f, _f, _p, _p]),
+    "vcb_op_nf4_roundtrip_f16": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p]),
     "vcb_splice_plan": (C.c_int, [_i32, _p, _i32, _i32, _i32, _i32, _p, _p, _i64, _p]),
     "vcb_create": (C.c_int, [C.POINTER(VcbConfig), _i32, C.POINTER(_p)]),
     "vcb_destroy": (C.c_int, [_p]),

@@ -70,9 +70,13 @@ class Engine:
             pass
 
     # ------------------------------------------------------------------------------------------------
-    def bind(self, state_dict: Dict[str, torch.Tensor], chunk: int = 64) -> None:
-        """Copies (and packs) the named tensors into the handle; the caller may drop its copies afterwards."""
+    def bind(self, state_dict: Dict[str, torch.Tensor], chunk: int = 64, nf4: bool = False) -> None:
+        """Copies (and packs) the named tensors into the handle; the caller may drop its copies afterwards.
+        nf4=True (`load_4bit`): the weights bitsandbytes would hold as NF4 `Linear4bit` layers are replaced by their
+        de-quantised fp16 values on the way in (vcoder_b200/nf4.py, vcb_op_nf4_roundtrip_f16)."""
         items = [(k, v) for k, v in state_dict.items() if torch.is_tensor(v) and v.dtype.is_floating_point]
+        if nf4:
+            from . import nf4 as _nf4
         for i in range(0, len(items), chunk):
             part = items[i:i + chunk]
             keep = []
@@ -82,6 +86,9 @@ class Engine:
                 if t.dtype != torch.float16:
                     t = t.to(torch.float16)
                 t = t.contiguous()
+                if nf4 and _nf4.is_bnb_linear(k):
+                    t = t.to(self.tdev, copy=True)
+                    _nf4.nf4_roundtrip_(t)
                 keep.append(t)
                 arr[j].name = k.encode()
                 arr[j].data = t.data_ptr()

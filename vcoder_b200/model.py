@@ -75,9 +75,10 @@ class _VCoderBase:
     model_type = "vcoder_ds_llava"
 
     def __init__(self, g: ModelGeometry, state_dict: Optional[Dict[str, torch.Tensor]] = None, max_batch: int = 8,
-                 max_seq_len: int = 2048, device: int = 0, image_processor=None):
+                 max_seq_len: int = 2048, device: int = 0, image_processor=None, load_4bit: bool = False):
         g = g.with_variant(self.variant)
         self.geometry = g
+        self.load_4bit = load_4bit  # builder.py:30-37: NF4 + double quantisation, compute dtype fp16 (vcoder_b200/nf4.py)
         self._eng = Engine(g, max_batch=max_batch, max_seq_len=max_seq_len, device=device)
         self._tower = CLIPVisionTower(self._eng, g, image_processor)
         self.config = types.SimpleNamespace(
@@ -100,7 +101,10 @@ class _VCoderBase:
 
     # ---- nn.Module-ish surface the callers touch (builder.py:139-153) -----------------------------------------
     def load_state_dict(self, state_dict, strict: bool = False):
-        self._eng.bind(state_dict)
+        if self.load_4bit:
+            self._eng.bind(state_dict, nf4=True)
+        else:
+            self._eng.bind(state_dict)
         return self
 
     def eval(self):
