@@ -187,3 +187,38 @@ def test_lora_checkpoint_is_merged_without_peft(tmp_path, monkeypatch):
     want = w0 + ((B.half() @ A.half()) * (alpha / r)).half()
     assert torch.equal(got, want) and not torch.equal(got, w0)
     assert torch.equal(RecordingEngine.last.tensors["model.mm_projector.0.weight"], sd["model.mm_projector.0.weight"])
+
+
+def test_ragged_batch_is_split_into_equal_length_groups(monkeypatch):
+    """f3 remainder: a batch whose spliced lengths differ (the reference: NameError, vcoder_ds_llava_arch.py:292-300) runs as
+    groups of equal spliced length, rows keep their own images; `ragged_batches = False` restores the NameError."""
+    from vcoder_b200 import model as model_mod
+    from vcoder_b200._lib import VcbError
+    from vcoder_b200.engine import splice_plan
+
+    class Eng(RecordingEngine):
+        calls = []
+
+        def set_sampling(self, *a, **k):
+            pass
+
+        def generate(self, ids, images, segs, depths, max_new_tokens):
+            try:
+                splice_plan(synth.VARIANT_VCODER_DS, ids.numpy(), self.g.n_patches, True, [True] * ids.shape[0])
+            except VcbError:
+                raise
+            Eng.calls.append((ids[:, 0].tolist(), images[:, 0, 0, 0].tolist()))
+            return ids[:, :1].repeat(1, max_new_tokens)
+
+    monkeypatch.setattr("vcoder_b200.model.Engine", Eng)
+    g = synth.PRESETS["tiny"]
+    m = model_mod.VCoderDSLlavaLlamaForCausalLM(g, None, max_batch=4, max_seq_len=4096)
+    I, S = synth.IMAGE_TOKEN_INDEX, synth.SEG_TOKEN_INDEX
+    ids = torch.tensor([[1, I, S, 7], [9, 5, 6, 7], [2, I, S, 8], [3, 4, 5, 6]])
+    px = torch.arange(4, dtype=torch.float32).view(4, 1, 1, 1).expand(4, 3, 56, 56).contiguous()
+    out = m.generate(ids, images=px, segs=px, depths=px + 1, max_new_tokens=2)
+    assert out[:, 4:].tolist() == [[1, 1], [9, 9], [2, 2], [3, 3]]
+    assert sorted(Eng.calls) == [([1, 2], [0.0, 2.0]), ([9, 3], [1.0, 3.0])]  # two groups, each row with its own image
+    m.ragged_batches = False
+    with pytest.raises(NameError):
+        m.generate(ids, images=px, segs=px, depths=px + 1, max_new_tokens=2)

@@ -89,8 +89,15 @@ def test_reference_error_behaviour():
     sd2 = synth.make_state_dict(g.with_variant(synth.VARIANT_VCODER_DS), seed=0)
     m2 = VCoderDSLlavaLlamaForCausalLM(g, sd2, max_batch=2, max_seq_len=128)
     im2, sg2 = synth.make_pixels(g, 2, 1), synth.make_pixels(g, 2, 2)
-    with pytest.raises(NameError):  # ragged batch
-        m2.generate(torch.tensor([[1, I, S, 7], [1, 5, 6, 7]]), images=im2, segs=sg2, depths=im2, max_new_tokens=2)
+    # ragged batch (spliced lengths differ): the reference dies with NameError; here every row gets what it would get alone
+    ragged = torch.tensor([[1, I, S, 7], [1, 5, 6, 7]])
+    got = m2.generate(ragged, images=im2, segs=sg2, depths=im2, max_new_tokens=3)
+    for b in range(2):
+        alone = m2.generate(ragged[b:b + 1], images=im2[b:b + 1], segs=sg2[b:b + 1], depths=im2[b:b + 1], max_new_tokens=3)
+        assert torch.equal(got[b:b + 1], alone)
+    m2.ragged_batches = False
+    with pytest.raises(NameError):  # the reference's behaviour (vcoder_ds_llava_arch.py:292-300)
+        m2.generate(ragged, images=im2, segs=sg2, depths=im2, max_new_tokens=2)
     with pytest.raises(ValueError):  # HF: `temperature` has to be a strictly positive float
         m2.generate(torch.tensor([[1, I, S, 7]]), images=images, segs=segs, do_sample=True, temperature=0.0, max_new_tokens=2)
     with pytest.raises(NotImplementedError):

@@ -94,6 +94,7 @@ class _VCoderBase:
         # f3: interactive callers (serve/cli.py loop, serve/chat.py:41-159) re-send the whole conversation and every image
         # each turn; with the prefix cache the towers are skipped for unchanged pixels and only the new part of the prompt
         # is prefilled.  `last_prefill` reports what the most recent interactive generate() reused.
+        self.ragged_batches = True  # f3: batches of different spliced lengths are split into equal-length groups (see _generate_ragged)
         self.prefix_cache = True
         self.last_prefill = {"spliced_len": 0, "reused_len": 0, "towers_skipped": False}
         if state_dict is not None:
@@ -135,6 +136,36 @@ class _VCoderBase:
 
     def get_vision_tower(self):
         return self._tower
+
+    # ---- f3 remainder: batches whose spliced lengths differ -----------------------------------------------------------
+    def _generate_ragged(self, input_ids, images, segs, depths, max_new_tokens):
+        """The reference pads such a batch (vcoder_ds_llava_arch.py:278-300) and then dies with NameError (`_new_labels`
+        is unset when labels is None).  Here the rows are grouped by spliced length (host planner, one row at a time) and
+        every group runs through the engine as its own batch — each sequence gets exactly the tokens it would get alone;
+        `ragged_batches = False` restores the reference's NameError."""
+        from .engine import splice_plan
+        P = self.geometry.n_patches
+        ids_h = input_ids.detach().cpu().long()
+        B = ids_h.shape[0]
+
+        def nz(t, b):  # `mean(x) == 0` on the fp16 image, as is_depth_zero / is_seg_zero (arch.py:161, it arch.py:148)
+            return bool(t[b].to(torch.float16).float().mean().to(torch.float16) != 0)
+
+        groups = {}
+        for b in range(B):
+            flag = None
+            if self.variant == synth.VARIANT_VCODER_DS and depths is not None:
+                flag = [nz(depths, b)]
+            elif self.variant == synth.VARIANT_VCODER_IT and segs is not None:
+                flag = [nz(segs, b)]
+            plan = splice_plan(self.variant, ids_h[b:b + 1].numpy(), P, segs is not None, flag)
+            groups.setdefault(plan.shape[1], []).append(b)
+        out = torch.zeros(B, max_new_tokens, dtype=torch.int64)
+        for _, rows in sorted(groups.items()):
+            idx = torch.tensor(rows)
+            pick = lambda t: None if t is None else (torch.stack([t[r] for r in rows]) if isinstance(t, (list, tuple)) else t[idx.to(t.device)])
+            out[idx] = self._eng.generate(ids_h[idx], pick(images), pick(segs), pick(depths), max_new_tokens=max_new_tokens).cpu()
+        return out
 
     # ---- a2: encoders -------------------------------------------------------------------------------------------
     def encode_images(self, images):
@@ -202,7 +233,12 @@ class _VCoderBase:
         interactive = streamer is not None or bool(stopping_criteria) or eos_token_id is not None
         try:
             if not interactive:
-                new = self._eng.generate(input_ids, images, segs, depths, max_new_tokens=max_new_tokens)
+                try:
+                    new = self._eng.generate(input_ids, images, segs, depths, max_new_tokens=max_new_tokens)
+                except VcbError as e:
+                    if e.code != -5 or not self.ragged_batches or B < 2:
+                        raise
+                    new = self._generate_ragged(input_ids, images, segs, depths, max_new_tokens)
                 return torch.cat([input_ids.to(dev), new.to(dev)], dim=1)
             # token-by-token: TextStreamer / KeywordsStoppingCriteria (mm_utils.py:128-151) / eos need host ids.  The
             # GPU keeps `lookahead` steps queued while Python looks at a token (vcb_decode_stream).
