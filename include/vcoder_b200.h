@@ -244,6 +244,22 @@ int vcb_prefill(vcb_handle h, const int64_t* ids_host, int32_t B, int32_t T, con
                 const vcb_half* segs_any, const vcb_half* depths_any, int32_t* next_ids_any, vcb_half* last_logits_any,
                 vcb_half* embeds_any, int32_t* spliced_len_host, void* stream);
 
+/* The forward() seam: VCoderDSLlavaLlamaForCausalLM.forward(input_ids, images=, segs=, depths=) with labels = None and
+ * past_key_values = None (language_model/vcoder_ds_llava_llama.py:57-118; CausalLMOutputWithPast.logits).  Same inputs
+ * as vcb_prefill; logits_dev (DEVICE memory, logits_halves >= B * T' * V fp16 elements; T' from vcb_splice_plan)
+ * receives lm_head(norm(hidden)) of EVERY spliced position, row-major [B, T', V].  The KV cache is filled and the first
+ * greedy token selected exactly as by vcb_prefill, so vcb_decode may follow.  VCB_ERR_NOMEM when the buffer is small. */
+int vcb_forward_logits(vcb_handle h, const int64_t* ids_host, int32_t B, int32_t T, const vcb_half* images_any,
+                       const vcb_half* segs_any, const vcb_half* depths_any, vcb_half* logits_dev, int64_t logits_halves,
+                       int32_t* spliced_len_host, void* stream);
+
+/* The prepare_inputs_labels_for_multimodal seam (vcoder_ds_llava_arch.py:126-314; its `new_input_embeds` result):
+ * towers + projectors + splice only.  embeds_any [B, T', H] fp16 (host or device).  No decoder pass, no KV: the handle
+ * is left un-prefilled (vcb_decode fails until the next vcb_prefill). */
+int vcb_splice_embeds(vcb_handle h, const int64_t* ids_host, int32_t B, int32_t T, const vcb_half* images_any,
+                      const vcb_half* segs_any, const vcb_half* depths_any, vcb_half* embeds_any,
+                      int32_t* spliced_len_host, void* stream);
+
 /* vcb_prefill for multi-turn callers.  serve/chat.py:41-159 (Chat.generate_stream) and the
  * serve/cli.py:80-135 loop re-tokenise the WHOLE conversation and re-send every image on every turn, and
  * prepare_inputs_for_generation re-threads images/segs/depths (vcoder_ds_llava_llama.py:137-139), so the reference

@@ -222,3 +222,41 @@ def test_ragged_batch_is_split_into_equal_length_groups(monkeypatch):
     m.ragged_batches = False
     with pytest.raises(NameError):
         m.generate(ids, images=px, segs=px, depths=px + 1, max_new_tokens=2)
+
+
+def test_forward_and_prepare_inputs_seams_host_logic(monkeypatch):
+    """The mirror's forward() / prepare_inputs_labels_for_multimodal (section 8b seams) without a GPU: result types, the
+    left-grown attention mask (vcoder_ds_llava_arch.py:308-311), the early return (:130-133) and the refused arguments."""
+    from vcoder_b200 import model as model_mod
+
+    class Eng(RecordingEngine):
+        def splice_embeds(self, ids, images, segs, depths):
+            return torch.zeros(ids.shape[0], ids.shape[1] - 2 + 2 * self.g.n_patches, self.g.llm_hidden, dtype=torch.float16)
+
+        def forward_logits(self, ids, images, segs, depths):
+            return torch.ones(ids.shape[0], ids.shape[1] - 2 + 2 * self.g.n_patches, self.g.llm_vocab, dtype=torch.float16)
+
+    monkeypatch.setattr("vcoder_b200.model.Engine", Eng)
+    g = synth.PRESETS["tiny"]
+    m = model_mod.VCoderDSLlavaLlamaForCausalLM(g, None, max_batch=2, max_seq_len=256)
+    I, S = synth.IMAGE_TOKEN_INDEX, synth.SEG_TOKEN_INDEX
+    ids = torch.tensor([[1, I, S, 7], [2, I, S, 8]])
+    px = torch.zeros(2, 3, 56, 56)
+    mask = torch.ones(2, 4, dtype=torch.long)
+    r_ids, r_mask, r_pkv, r_emb, r_lab = m.prepare_inputs_labels_for_multimodal(ids, mask, None, None, px, px, px)
+    Tp = 2 + 2 * g.n_patches
+    assert r_ids is None and r_pkv is None and r_lab is None and r_emb.shape == (2, Tp, g.llm_hidden)
+    assert r_mask.shape == (2, Tp) and r_mask.dtype == mask.dtype and bool(r_mask.all())
+    same = m.prepare_inputs_labels_for_multimodal(ids[:, :1], mask, ((0, 0),), None, None, None, None)
+    assert same[0].shape == (2, 1) and same[2] == ((0, 0),) and same[3] is None
+    out = m(input_ids=ids, images=px, segs=px, depths=px)
+    assert type(out).__name__ == "CausalLMOutputWithPast" and out.logits.shape == (2, Tp, g.llm_vocab) and out.loss is None
+    assert out.past_key_values is None
+    assert m.forward(input_ids=ids, images=px, segs=px, depths=px, return_dict=False)[0].shape == (2, Tp, g.llm_vocab)
+    for bad in ({"labels": ids}, {"inputs_embeds": r_emb}, {"past_key_values": ((0, 0),)}, {"output_hidden_states": True}):
+        with pytest.raises(NotImplementedError):
+            m(input_ids=ids, images=px, **bad)
+    with pytest.raises(NotImplementedError):
+        m(input_ids=ids, images=px, attention_mask=torch.tensor([[0, 1, 1, 1], [1, 1, 1, 1]]))
+    with pytest.raises(TypeError):
+        model_mod.VCoderLlavaLlamaForCausalLM(g, None, max_batch=2, max_seq_len=256)(input_ids=ids, images=px, depths=px)

@@ -71,6 +71,8 @@ SIGNATURES = {
     "vcb_tower_forward": (C.c_int, [_p, _p, _i32, _p, _p]),
     "vcb_encode": (C.c_int, [_p, _i32, _p, _i32, _p, _p]),
     "vcb_prefill": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "vcb_forward_logits": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _p, C.c_int64, _p, _p]),
+    "vcb_splice_embeds": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _p, _p, _p]),
     "vcb_prefill_cached": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "vcb_prefix_match": (C.c_int, [_p, _i32, _p, _i32, _i32, _i32, _i32, _p]),
     "vcb_decode": (C.c_int, [_p, _i32, _p, _p, _p]),

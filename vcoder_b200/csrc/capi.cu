@@ -304,6 +304,36 @@ int vcb_prefill(vcb_handle h, const int64_t* ids, int32_t B, int32_t T, const vc
   return kOk;
 }
 
+int vcb_forward_logits(vcb_handle h, const int64_t* ids, int32_t B, int32_t T, const vcb_half* images,
+                       const vcb_half* segs, const vcb_half* depths, vcb_half* logits_dev, int64_t logits_halves,
+                       int32_t* spliced_len, void* stream) {
+  VCB_CHECK(h != nullptr, kErrInvalid, "null handle");
+  VCB_CHECK(logits_dev != nullptr && logits_halves > 0, kErrInvalid, "vcb_forward_logits: no logits buffer");
+  int len = 0;
+  StreamGuard sg(h->e, ST(stream));
+  PrefillExtra ex;
+  ex.all_logits = logits_dev;
+  ex.all_logits_halves = static_cast<long>(logits_halves);
+  VCB_TRY(engine_prefill(h->e, ids, B, T, images, segs, depths, false, nullptr, nullptr, nullptr, &len, nullptr, nullptr,
+                         sg.st, &ex));
+  if (spliced_len) *spliced_len = len;
+  return kOk;
+}
+
+int vcb_splice_embeds(vcb_handle h, const int64_t* ids, int32_t B, int32_t T, const vcb_half* images,
+                      const vcb_half* segs, const vcb_half* depths, vcb_half* embeds, int32_t* spliced_len, void* stream) {
+  VCB_CHECK(h != nullptr, kErrInvalid, "null handle");
+  VCB_CHECK(embeds != nullptr, kErrInvalid, "vcb_splice_embeds: no embeds buffer");
+  int len = 0;
+  StreamGuard sg(h->e, ST(stream));
+  PrefillExtra ex;
+  ex.embeds_only = true;
+  VCB_TRY(engine_prefill(h->e, ids, B, T, images, segs, depths, false, nullptr, nullptr, embeds, &len, nullptr, nullptr,
+                         sg.st, &ex));
+  if (spliced_len) *spliced_len = len;
+  return kOk;
+}
+
 int vcb_prefill_cached(vcb_handle h, const int64_t* ids, int32_t B, int32_t T, const vcb_half* images,
                        const vcb_half* segs, const vcb_half* depths, int32_t* next_ids, vcb_half* last_logits,
                        int32_t* spliced_len, int32_t* reused_len, int32_t* towers_skipped, void* stream) {

@@ -651,7 +651,7 @@ int prefix_match_host(const int32_t* cached, int cached_len, const int32_t* plan
 
 int engine_prefill(Engine* e, const int64_t* ids, int B, int T, const void* images, const void* segs,
                    const void* depths, bool reuse, void* next_ids_out, void* last_logits_out, void* embeds_out,
-                   int* spliced_len, int* reused_len, int* towers_skipped, cudaStream_t st) {
+                   int* spliced_len, int* reused_len, int* towers_skipped, cudaStream_t st, const PrefillExtra* extra) {
   const vcb_config& c = e->cfg;
   VCB_CHECK(ids != nullptr && B >= 1 && B <= c.max_batch && T >= 1, kErrInvalid, "vcb_prefill: bad ids / batch");
   VCB_CUDA(cudaSetDevice(e->device));
@@ -768,6 +768,14 @@ int engine_prefill(Engine* e, const int64_t* ids, int B, int T, const void* imag
   __half* x = e->x.as<__half>();
   VCB_TRY(splice_gather(e->plan_dev.as<int32_t>(), e->embed.as<__half>(), e->feats.as<__half>(), x, rows, H, st));
   if (embeds_out) VCB_TRY(copy_any(embeds_out, x, rows * H * 2, st));
+  if (extra && extra->embeds_only) return kOk;  // prepare_inputs_labels_for_multimodal seam: the handle stays un-prefilled
+  if (extra && extra->all_logits) {
+    VCB_CHECK(extra->all_logits_halves >= rows * V, kErrNoMem, "vcb_forward_logits: logits buffer smaller than B * T' * V");
+    cudaPointerAttributes pa;
+    VCB_CUDA(cudaPointerGetAttributes(&pa, extra->all_logits));
+    VCB_CHECK(pa.type == cudaMemoryTypeDevice || pa.type == cudaMemoryTypeManaged, kErrInvalid,
+              "vcb_forward_logits: the logits buffer must be device memory");
+  }
 
   // ---- KV pages for the prompt (the page ids of a sequence never change, so a reused prefix stays where it is)
   if (L0 == 0) e->pages_per_seq_alloc = 0;
@@ -812,6 +820,25 @@ int engine_prefill(Engine* e, const int64_t* ids, int B, int T, const void* imag
       GemmEpilogue ep;
       ep.C = x; ep.ldc = H; ep.residual = x; ep.ldr = H;
       VCB_TRY(gemm_f16(e->mid.as<__half>(), FF, l.down_w.as<__half>(), FF, rows, H, FF, ep, 0, st));
+    }
+  }
+  // ---- forward() seam: logits of every position (final RMSNorm over all rows, then the tcgen05 GEMM against lm_head; a
+  //      vocabulary or width the tile shapes do not divide goes through the weight-streaming GEMM 32 rows at a time)
+  if (extra && extra->all_logits) {
+    __half* out = static_cast<__half*>(extra->all_logits);
+    if (V % 32 == 0 && H % 64 == 0) {
+      VCB_TRY(rmsnorm_f16(x, e->final_norm.as<__half>(), xn, rows, H, c.llm_rms_eps, st));
+      GemmEpilogue ep;
+      ep.C = out; ep.ldc = V;
+      VCB_TRY(gemm_f16(xn, H, e->lm_head.as<__half>(), H, rows, V, H, ep, 0, st));
+    } else {
+      for (long r0 = 0; r0 < rows; r0 += 32) {
+        SkinnyParams s;
+        s.norm_w = e->final_norm.as<__half>(); s.norm_eps = c.llm_rms_eps;
+        s.X = x + r0 * H; s.ldx = H; s.W = e->lm_head.as<__half>(); s.Wp = e->lm_head_p.as<__half>(); s.Y = out + r0 * V; s.ldy = V;
+        s.B = static_cast<int>(std::min<long>(32, rows - r0)); s.N = V; s.K = H;
+        VCB_TRY(skinny_gemm(s, st));
+      }
     }
   }
   // ---- logits for the LAST position only (the reference computes all T' rows and greedy reads [:, -1])

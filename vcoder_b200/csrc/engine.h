@@ -108,9 +108,18 @@ int engine_project(Engine* e, int row_begin, int row_end, const ProjW& w, cudaSt
 // reuse = false: every call runs the towers and the whole prompt (vcb_prefill).  reuse = true (vcb_prefill_cached): the
 // towers are skipped when the pixels' fingerprint equals the previous call's, and only the part of the spliced prompt
 // behind the longest prefix it shares with the sequence already in the KV cache runs through the decoder.
+// `extra` (optional) serves the forward() / prepare_inputs_labels_for_multimodal seams: embeds_only stops after the
+// splice (no decoder, no KV; the handle is left un-prefilled); all_logits receives final-norm + lm_head of EVERY spliced
+// position, [B, T', V] fp16, and must hold all_logits_halves >= B * T' * V halves (device memory).
+struct PrefillExtra {
+  bool embeds_only = false;
+  void* all_logits = nullptr;
+  long all_logits_halves = 0;
+};
 int engine_prefill(Engine* e, const int64_t* ids_host, int B, int T, const void* images, const void* segs,
                    const void* depths, bool reuse, void* next_ids_out, void* last_logits_out, void* embeds_out,
-                   int* spliced_len, int* reused_len, int* towers_skipped, cudaStream_t st);
+                   int* spliced_len, int* reused_len, int* towers_skipped, cudaStream_t st,
+                   const PrefillExtra* extra = nullptr);
 // Host-only part of the prefix cache: longest prefix (<= limit) shared by every row of `cached` [B][cached_len] and
 // `plan` [B][plan_len]; visual rows (entries <= -2) only count when `features_same`.
 int prefix_match_host(const int32_t* cached, int cached_len, const int32_t* plan, int plan_len, int B, int features_same,

@@ -165,6 +165,39 @@ class Engine:
             out["embeds"] = embeds.view(-1)[: B * slen.value * self.g.llm_hidden].view(B, slen.value, self.g.llm_hidden)
         return out
 
+    def forward_logits(self, ids: torch.Tensor, images=None, segs=None, depths=None) -> torch.Tensor:
+        """vcb_forward_logits: lm_head(norm(hidden)) of EVERY spliced position, [B, T', V] fp16 on the device (the
+        `logits` of the reference's forward(), vcoder_ds_llava_llama.py:95-118).  Fills the KV cache like prefill."""
+        ids_h = ids.detach().to("cpu", torch.int64).contiguous()
+        B, T = ids_h.shape
+        self._last_batch = B
+        im, sg, dp = _as_half_any(images), _as_half_any(segs), _as_half_any(depths)
+        for t, what in ((im, "images"), (sg, "segs"), (dp, "depths")):
+            self._check_pixels(t, what, B)
+        t_max = T + (3 * self.g.n_patches if im is not None else 0)
+        logits = torch.empty(B * t_max * self.g.llm_vocab, dtype=torch.float16, device=self.tdev)
+        slen = C.c_int32(0)
+        with self.lock:
+            _lib.check(self.lib.vcb_forward_logits(self.h, _lib.ptr(ids_h), B, T, _lib.ptr(im), _lib.ptr(sg), _lib.ptr(dp),
+                                                   _lib.ptr(logits), logits.numel(), C.byref(slen), _stream_ptr()))
+        return logits[: B * slen.value * self.g.llm_vocab].view(B, slen.value, self.g.llm_vocab)
+
+    def splice_embeds(self, ids: torch.Tensor, images=None, segs=None, depths=None) -> torch.Tensor:
+        """vcb_splice_embeds: towers + projectors + splice only -> `new_input_embeds` [B, T', H] fp16 of
+        prepare_inputs_labels_for_multimodal (vcoder_ds_llava_arch.py:126-314).  Leaves the handle un-prefilled."""
+        ids_h = ids.detach().to("cpu", torch.int64).contiguous()
+        B, T = ids_h.shape
+        im, sg, dp = _as_half_any(images), _as_half_any(segs), _as_half_any(depths)
+        for t, what in ((im, "images"), (sg, "segs"), (dp, "depths")):
+            self._check_pixels(t, what, B)
+        t_max = T + (3 * self.g.n_patches if im is not None else 0)
+        embeds = torch.empty(B * t_max * self.g.llm_hidden, dtype=torch.float16, device=self.tdev)
+        slen = C.c_int32(0)
+        with self.lock:
+            _lib.check(self.lib.vcb_splice_embeds(self.h, _lib.ptr(ids_h), B, T, _lib.ptr(im), _lib.ptr(sg), _lib.ptr(dp),
+                                                  _lib.ptr(embeds), C.byref(slen), _stream_ptr()))
+        return embeds[: B * slen.value * self.g.llm_hidden].view(B, slen.value, self.g.llm_hidden)
+
     def decode(self, n_steps: int, want_logits=False):
         B = self._batch()
         ids = torch.empty(B, n_steps, dtype=torch.int32, device=self.tdev)

@@ -174,6 +174,58 @@ class _VCoderBase:
     def encode_seg_images(self, seg_images):
         return self._eng.encode(1, seg_images)
 
+    # ---- a4/a5 as callable seams: the two methods a maintainer would monkey-patch ------------
+    @torch.no_grad()
+    def prepare_inputs_labels_for_multimodal(self, input_ids, attention_mask, past_key_values, labels, images,
+                                             seg_images=None, depth_images=None):
+        """Same 5-tuple as vcoder_ds_llava_arch.py:126-314 for the inference callers (labels = None, no KV yet):
+        `(None, attention_mask, past_key_values, new_input_embeds, None)`; the text-only / single-token early return
+        (:130-133) hands the arguments back unchanged.  Towers, projectors and the splice run on the device."""
+        if labels is not None:
+            raise NotImplementedError("labels (training) are outside the inference path this engine replaces")
+        if images is None or input_ids.shape[1] == 1:
+            if past_key_values is not None and images is not None and input_ids.shape[1] == 1 and attention_mask is not None:
+                raise NotImplementedError("single-token steps run inside the engine (generate / Engine.decode)")
+            return input_ids, attention_mask, past_key_values, None, labels
+        if past_key_values is not None:
+            raise NotImplementedError("the engine owns the KV cache (multi-turn prompts: generate() with model.prefix_cache = True)")
+        if self.variant != synth.VARIANT_VCODER_DS and depth_images is not None:
+            raise TypeError("only VCoder-DS takes depth images")
+        embeds = self._eng.splice_embeds(input_ids, images, seg_images, depth_images).to(input_ids.device)
+        if attention_mask is not None:  # :308-311: the mask grows on the LEFT by the number of spliced-in positions
+            am = torch.as_tensor(attention_mask)
+            pad = torch.full((am.shape[0], embeds.shape[1] - input_ids.shape[1]), True, dtype=am.dtype, device=am.device)
+            attention_mask = torch.cat((pad, am), dim=1)
+            assert attention_mask.shape == embeds.shape[:2]
+        return None, attention_mask, past_key_values, embeds, None
+
+    @torch.no_grad()
+    def forward(self, input_ids=None, attention_mask=None, past_key_values=None, inputs_embeds=None, labels=None,
+                use_cache=None, output_attentions=None, output_hidden_states=None, images=None, segs=None, depths=None,
+                return_dict=None):
+        """forward() of language_model/vcoder_ds_llava_llama.py:57-118 for a whole prompt: logits of every spliced
+        position [B, T', V].  `past_key_values` of the result is None: the KV cache lives in the engine (filled by this
+        call; `Engine.decode` continues from it).  Training arguments (labels, inputs_embeds) are not served."""
+        if labels is not None or inputs_embeds is not None:
+            raise NotImplementedError("labels / inputs_embeds (training path) are outside the inference path")
+        if past_key_values is not None:
+            raise NotImplementedError("the engine owns the KV cache: use generate() / Engine.decode for the next tokens")
+        if output_attentions or output_hidden_states:
+            raise NotImplementedError("attention maps / hidden states are not materialised by the fused kernels")
+        if input_ids is None:
+            raise ValueError("forward() needs input_ids")
+        if attention_mask is not None and not bool(torch.as_tensor(attention_mask).bool().all()):
+            raise NotImplementedError("padded prompts: the reference itself mis-aligns the mask after the splice")
+        if self.variant != synth.VARIANT_VCODER_DS and depths is not None:
+            raise TypeError(f"{type(self).__name__}.forward() got an unexpected keyword argument 'depths'")
+        logits = self._eng.forward_logits(input_ids, images, segs, depths).to(input_ids.device)
+        if return_dict is False:
+            return (logits,)
+        from transformers.modeling_outputs import CausalLMOutputWithPast
+        return CausalLMOutputWithPast(loss=None, logits=logits, past_key_values=None, hidden_states=None, attentions=None)
+
+    __call__ = forward
+
     # ---- a5/a6 + f1: generate ----------------------------------------------------------------------------------
     @torch.no_grad()
     def generate(self, input_ids=None, images=None, segs=None, depths=None, do_sample: bool = False,
