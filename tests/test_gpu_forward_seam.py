@@ -78,7 +78,7 @@ def test_forward_and_prepare_inputs_against_reference_golden(variant, name, fnam
     assert isinstance(tup, tuple) and torch.equal(tup[0], res.logits)  # deterministic
     # forward() fills the KV cache and selects the first token like a prefill: decoding continues from it
     n_new = z["greedy_ids"].shape[1]
-    dec_ids, _ = model._eng.decode(n_new - 1)
+    dec_ids = model._eng.decode(n_new - 1)
     assert np.array_equal(dec_ids.cpu().numpy(), z["greedy_ids"][:, 1:])
     # training arguments are refused, not ignored
     for bad in ({"labels": ids}, {"inputs_embeds": r_embeds}, {"past_key_values": ((None, None),)}, {"output_attentions": True}):

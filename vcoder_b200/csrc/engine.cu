@@ -90,7 +90,7 @@ int engine_create(const vcb_config* c, int device, Engine** out) {
   VCB_CHECK(c->llm_hidden == c->llm_heads * 128, kErrInvalid, "LLaMA head_dim must be 128");
   VCB_CHECK(c->vit_hidden % 64 == 0 && c->vit_ffn % 64 == 0 && c->llm_hidden % 64 == 0 && c->llm_ffn % 64 == 0,
             kErrInvalid, "hidden / ffn sizes must be multiples of 64");
-  VCB_CHECK(c->llm_vocab % 32 == 0, kErrInvalid, "vocab must be a multiple of 32");
+  VCB_CHECK(c->llm_vocab % 16 == 0, kErrInvalid, "vocab must be a multiple of 16");
   VCB_CHECK(c->vit_image_size % c->vit_patch == 0, kErrInvalid, "image size must be a multiple of the patch size");
   VCB_CHECK(c->kv_page_tokens == 64, kErrInvalid, "kv_page_tokens must be 64");
   VCB_CHECK(c->max_batch >= 1 && c->max_batch <= 32, kErrInvalid, "max_batch must be in [1, 32]");
