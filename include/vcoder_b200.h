@@ -331,7 +331,9 @@ int vcb_profile_read(float* ms_by_category, uint64_t* launches_by_category, int3
 /* Hardware micro-benchmarks that size the attention kernels (tools/microbench.py; never called by the engine).
  * which = 0: TMEM -> register read rate with `warps` warps per CTA and `param` tcgen05.ld.32x32b.x32 in flight per warp;
  * *result = bytes per clock per SM.  which = 1: MUFU ex2.approx rate (param != 0: one FFMA between the ex2);
- * *result = ex2 per clock per SM.  which = 2: the packed ex2.approx.f16x2 (exponentials per clock per SM). */
+ * *result = ex2 per clock per SM.  which = 2: the packed ex2.approx.f16x2 (exponentials per clock per SM).
+ * which = 3: the exponential / pack / store loop of the ViT attention softmax in isolation (param bit 0: no row sums,
+ * bit 1: no shared-memory stores, bit 2: software-skewed); *result = exponentials per clock per SM. */
 int vcb_microbench(int32_t which, int32_t warps, int32_t param, int32_t iters, float* result);
 
 /* Tuning hook (tools/bench_decode.py): pipeline shape of the weight-streaming kernel for GEMMs with this (N, K): `warps`

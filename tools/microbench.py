@@ -21,3 +21,9 @@ for warps in (4, 8, 16, 32):
 for warps in (4, 8, 16):
     _lib.check(lib.vcb_microbench(2, warps, 0, 4000, C.byref(r)))
     print(json.dumps({"bench": "ex2_f16x2", "warps": warps, "ex2_per_clk_per_sm": round(r.value, 2)}))
+VARIANTS = {0: "as in the kernel", 1: "no row sums", 2: "no P stores", 3: "no sums, no stores", 4: "skewed by 16", 5: "skewed, no sums",
+            6: "skewed, no stores", 7: "skewed, no sums, no stores"}
+for warps in (4, 8):
+    for var in range(8):
+        _lib.check(lib.vcb_microbench(3, warps, var, 2000, C.byref(r)))
+        print(json.dumps({"bench": "softmax_exp_loop", "warps": warps, "variant": VARIANTS[var], "ex2_per_clk_per_sm": round(r.value, 2)}))

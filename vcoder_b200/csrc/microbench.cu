@@ -90,6 +90,72 @@ __global__ void ex2_h2_bench_kernel(int iters, unsigned long long* cycles, float
   if (s == 0x12345678u) sink[0] = 1.f;
 }
 
+// The exponential / pack / store loop of the ViT attention softmax (attn_vit_pair.cu) in isolation: every thread owns one
+// 64-score half row in registers and writes its 128-byte P row (swizzled 16-byte chunks) per round.  variant bit 0: no row
+// sums; bit 1: no shared-memory stores; bit 2: sums / packs placed 16 exponentials behind their MUFU (software skew).
+template <int kVariant>
+__global__ void softmax_loop_bench_kernel(int iters, unsigned long long* cycles, float* sink) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  uint32_t v[2][32];
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[c][i] = __float_as_uint(-0.01f * static_cast<float>((threadIdx.x * 7 + c * 32 + i) & 255));
+  const int r = threadIdx.x & 127;
+  uint8_t* prow = sm + (threadIdx.x >> 7) * 16384 + r * 128;
+  float L = 0.f;
+  const float sc = 0.18f;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    const float msc = 0.001f * static_cast<float>(it & 15);
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t pk[16];
+      if (kVariant & 4) {
+        constexpr int kSkew = 16;
+        float e[32];
+#pragma unroll
+        for (int i = 0; i < 32 + kSkew; i += 2) {
+          if (i < 32) {
+            e[i] = fast_exp2(fmaf(__uint_as_float(v[c][i]), sc, -msc));
+            e[i + 1] = fast_exp2(fmaf(__uint_as_float(v[c][i + 1]), sc, -msc));
+          }
+          if (i >= kSkew) {
+            const int j = i - kSkew;
+            if (!(kVariant & 1)) { l0 += e[j]; l1 += e[j + 1]; }
+            pk[j >> 1] = pack_half2(e[j], e[j + 1]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(v[c][i]), sc, -msc));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(v[c][i + 1]), sc, -msc));
+          if (!(kVariant & 1)) { l0 += p0; l1 += p1; }
+          pk[i >> 1] = pack_half2(p0, p1);
+        }
+      }
+      if (!(kVariant & 2)) {
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const int chunk = (c * 4 + w) ^ (r & 7);
+          *reinterpret_cast<uint4*>(prow + (chunk << 4)) = make_uint4(pk[4 * w], pk[4 * w + 1], pk[4 * w + 2], pk[4 * w + 3]);
+        }
+      } else {
+#pragma unroll
+        for (int w = 0; w < 16; ++w) l1 += __uint_as_float(pk[w] & 0x3f800000u);
+      }
+    }
+    L += l0 + l1;
+  }
+  __syncthreads();
+  const long long t1 = clock64();
+  if (threadIdx.x == 0) cycles[blockIdx.x] = static_cast<unsigned long long>(t1 - t0);
+  if (L == 123.456f) sink[0] = L + static_cast<float>(sm[threadIdx.x]);
+}
+
 }  // namespace
 
 // which = 0: TMEM read, returns bytes per clock per SM; which = 1: ex2 (param = with_fma), returns ex2 per clock per SM
@@ -107,6 +173,16 @@ int microbench(int which, int warps, int param, int iters, float* result) {
       else tmem_read_bench_kernel<4><<<n_sm, warps * 32>>>(iters, cyc, static_cast<uint32_t*>(sink));
     } else if (which == 1) {
       ex2_bench_kernel<<<n_sm, warps * 32>>>(iters, param, cyc, static_cast<float*>(sink));
+    } else if (which == 3) {
+      const size_t smb = static_cast<size_t>((warps + 3) / 4) * 16384;
+      float* sk = static_cast<float*>(sink);
+#define VCB_SLB(V)                                                                                                  \
+  case V:                                                                                                           \
+    cudaFuncSetAttribute(softmax_loop_bench_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072);        \
+    softmax_loop_bench_kernel<V><<<n_sm, warps * 32, smb>>>(iters, cyc, sk);                                        \
+    break;
+      switch (param & 7) { VCB_SLB(0) VCB_SLB(1) VCB_SLB(2) VCB_SLB(3) VCB_SLB(4) VCB_SLB(5) VCB_SLB(6) VCB_SLB(7) }
+#undef VCB_SLB
     } else {
       ex2_h2_bench_kernel<<<n_sm, warps * 32>>>(iters, cyc, static_cast<float*>(sink));
     }
@@ -124,6 +200,8 @@ int microbench(int which, int warps, int param, int iters, float* result) {
     *result = static_cast<float>(static_cast<double>(warps) * iters * ilp * 4096.0 / avg);
   } else if (which == 1) {
     *result = static_cast<float>(static_cast<double>(warps) * 32 * iters * 8.0 / avg);
+  } else if (which == 3) {
+    *result = static_cast<float>(static_cast<double>(warps) * 32 * iters * 64.0 / avg);  // exponentials per clock per SM
   } else {
     *result = static_cast<float>(static_cast<double>(warps) * 32 * iters * 16.0 / avg);  // two exponentials per instruction
   }
