@@ -302,3 +302,24 @@ def test_reference_seg_eval_model_runs_unmodified_on_vcoder(rig):
         assert len(pre) == 1 and pre[0][2] and pre[0][3] and not pre[0][4]  # images + segs, no depths
         assert [int(t) for t in pre[0][1][0] if t < 0] == [I, S]  # tokenizer_seg_token emits [IMAGE, SEG] (mm_utils.py:65-87)
         assert ("set_sampling", False, 1.0, 50, 1.0) in eng.calls
+
+
+def test_generate_batches_larger_than_the_handle_run_as_slices(monkeypatch):
+    """The reference's generate() takes any batch size; the handle holds `max_batch` sequences, so a larger batch runs
+    as consecutive slices (each with its own pixel rows) and the rows come back in order."""
+    from vcoder_b200.model import VCoderDSLlavaLlamaForCausalLM
+    FakeEngine.instances = []
+    monkeypatch.setattr("vcoder_b200.model.Engine", FakeEngine)
+    g = synth.PRESETS["tiny"].with_variant(synth.VARIANT_VCODER_DS)
+    model = VCoderDSLlavaLlamaForCausalLM(g, None, max_batch=4)
+    model.generation_config.eos_token_id = None
+    B, px_size = 10, g.vit_image_size
+    ids = torch.stack([torch.tensor([1, 5 + b, I, S, D, 9]) for b in range(B)])
+    px = [torch.randn(B, 3, px_size, px_size).half() for _ in range(3)]
+    out = model.generate(ids, images=px[0], segs=px[1], depths=px[2], do_sample=False, max_new_tokens=3)
+    eng = FakeEngine.instances[-1]
+    gens = [c for c in eng.calls if c[0] == "generate"]
+    assert [c[1].shape[0] for c in gens] == [4, 4, 2]
+    assert torch.equal(torch.cat([c[1] for c in gens]), ids)  # every row once, in order
+    assert out.shape == (B, ids.shape[1] + 3) and torch.equal(out[:, :ids.shape[1]], ids)
+    assert out[:, ids.shape[1]:].tolist() == [[11, 12, 13]] * B

@@ -285,12 +285,20 @@ class _VCoderBase:
         interactive = streamer is not None or bool(stopping_criteria) or eos_token_id is not None
         try:
             if not interactive:
-                try:
-                    new = self._eng.generate(input_ids, images, segs, depths, max_new_tokens=max_new_tokens)
-                except VcbError as e:
-                    if e.code != -5 or not self.ragged_batches or B < 2:
-                        raise
-                    new = self._generate_ragged(input_ids, images, segs, depths, max_new_tokens)
+                def run(rows):  # rows = None: the whole batch
+                    pick = lambda t: t if (t is None or rows is None) else t[rows.start:rows.stop]
+                    ids_r, im, sg, dp = pick(input_ids), pick(images), pick(segs), pick(depths)
+                    try:
+                        return self._eng.generate(ids_r, im, sg, dp, max_new_tokens=max_new_tokens)
+                    except VcbError as e:
+                        if e.code != -5 or not self.ragged_batches or ids_r.shape[0] < 2:
+                            raise
+                        return self._generate_ragged(ids_r, im, sg, dp, max_new_tokens)
+                mb = self._eng.max_batch
+                if B <= mb:
+                    new = run(None)
+                else:  # the reference takes any batch: more rows than the handle holds run as consecutive slices
+                    new = torch.cat([run(slice(b0, min(B, b0 + mb))).cpu() for b0 in range(0, B, mb)], dim=0)
                 return torch.cat([input_ids.to(dev), new.to(dev)], dim=1)
             # token-by-token: TextStreamer / KeywordsStoppingCriteria (mm_utils.py:128-151) / eos need host ids.  The
             # GPU keeps `lookahead` steps queued while Python looks at a token (vcb_decode_stream).
