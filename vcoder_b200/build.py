@@ -27,6 +27,8 @@ CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relax
 # ring-shape sweep, tcgen05 skinny GEMM, one-tile ViT attention, bulk-copy / cluster decode attention): DESIGN.md section 3.3
 if os.environ.get("VCB_EXPERIMENTAL", "0") not in ("", "0"):
     CFLAGS.append("-DVCB_EXPERIMENTAL=1")
+# VCB_EXTRA_CFLAGS: extra nvcc flags for diagnostic builds (e.g. -DVCB_VIT_DIAG=1: timing switches inside the ViT attention)
+CFLAGS += os.environ.get("VCB_EXTRA_CFLAGS", "").split()
 
 
 def _digest(paths) -> str:

@@ -203,6 +203,9 @@ attn_vit_pair_kernel(const __grid_constant__ CUtensorMap tm, VitPairParams p) {
         VCB_STAMP(2);
 
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#if defined(VCB_VIT_DIAG) && (VCB_VIT_DIAG & 4)
+        if (true) { mx0 = __uint_as_float(v[0][0]); } else
+#endif
         if (nk == kHalf) {
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
@@ -269,10 +272,17 @@ attn_vit_pair_kernel(const __grid_constant__ CUtensorMap tm, VitPairParams p) {
             if (nk >= (c + 1) * 32) {
 #pragma unroll
               for (int i = 0; i < 32; i += 2) {
+#if defined(VCB_VIT_DIAG) && (VCB_VIT_DIAG & 1)
+                const float p0 = fmaf(__uint_as_float(v[c][i]), sc, -msc);
+                const float p1 = fmaf(__uint_as_float(v[c][i + 1]), sc, -msc);
+#else
                 const float p0 = fast_exp2(fmaf(__uint_as_float(v[c][i]), sc, -msc));
                 const float p1 = fast_exp2(fmaf(__uint_as_float(v[c][i + 1]), sc, -msc));
+#endif
+#if !(defined(VCB_VIT_DIAG) && (VCB_VIT_DIAG & 8))
                 l0 += p0;
                 l1 += p1;
+#endif
                 pk[i >> 1] = pack_half2(p0, p1);
               }
             } else {
