@@ -101,16 +101,20 @@ attn_vit_pair_kernel(const __grid_constant__ CUtensorMap tm, VitPairParams p) {
   if (warp == kTmaWarp) {
     if (lane == 0) {
       tma_prefetch_desc(&tm);
-      for (int t = 0; t < ntiles; ++t) {
+      // request order = order of first use: Q_A, K_0 (-> S_A(0)), Q_B (-> S_B(0)), V_0, K_1, V_1, ...  (a 16 KiB box of
+      // 128-byte rows takes ~500 cycles to arrive: profiles/r02_vit_pair_diag.txt)
+      auto load_q = [&](int t) {
         mbar_expect_tx(bar(kBarQ + t), kTile);
         tma_load_2d(base + t * kTile, &tm, bar(kBarQ + t), h * kDh, row_base + q0[t]);
-      }
+      };
+      load_q(0);
       for (int j = 0; j < nb; ++j) {
         const int slot = j & 1;
         const uint32_t ph = static_cast<uint32_t>(((j >> 1) - 1) & 1);
         if (j >= 2) mbar_wait(bar(kBarKEmpty + slot), ph);
         mbar_expect_tx(bar(kBarKFull + slot), kTile);
         tma_load_2d(base + kOffK + slot * kTile, &tm, bar(kBarKFull + slot), p.D + h * kDh, row_base + j * kKB);
+        if (j == 0 && ntiles == 2) load_q(1);
         if (j >= 2) mbar_wait(bar(kBarVEmpty + slot), ph);
         mbar_expect_tx(bar(kBarVFull + slot), kTile);
         tma_load_2d(base + kOffV + slot * kTile, &tm, bar(kBarVFull + slot), 2 * p.D + h * kDh, row_base + j * kKB);
@@ -237,8 +241,12 @@ attn_vit_pair_kernel(const __grid_constant__ CUtensorMap tm, VitPairParams p) {
           Mref = mblk;
           L *= f;
         }
-        // this half's P buffer was last read by PV(n-2)
-        if (n >= 2) {
+        // this half's P buffer was last read by PV(n-2).  Even halves need no barrier of their own: the S tile this half
+        // just waited for was committed by the same issuing thread AFTER it issued PV(n-2) (issue order PV(2j), S(j+1),
+        // PV(2j+1)), and a tcgen05.commit covers every MMA that thread issued before it.  (A completed mbarrier wait still
+        // costs 250-300 cycles here.)  The skipped phases are never waited for later: the rescale path and the epilogue
+        // only ever wait for the newest phase of a buffer's barrier.
+        if (n >= 2 && hf == 1) {
           mbar_wait(bar(kBarO + 2 * t + buf), ((n - 2) >> 1) & 1);
           tc_fence_after();
         }
