@@ -51,7 +51,7 @@ const char* get_thread_error();
 // -------------------------------------------------------------------------------------------------
 // GEMM (tcgen05): C[M,N] = epilogue(A[M,K] * W[N,K]^T)
 // -------------------------------------------------------------------------------------------------
-enum GemmAct : int { kActNone = 0, kActQuickGelu = 1, kActGeluErf = 2, kActSwiGLU = 3 };
+enum GemmAct : int { kActNone = 0, kActQuickGelu = 1, kActGeluErf = 2, kActSwiGLU = 3, kActRopeKv = 4 };
 
 struct GemmEpilogue {
   __half* C = nullptr;            // output, row-major, ldc elements per row
@@ -66,6 +66,15 @@ struct GemmEpilogue {
   // Residual-row remap (position embedding is indexed by patch, not by image):
   //   res_row = res_mod ? (m % res_mod) + res_off : out_row
   int res_mod = 0, res_off = 0;
+  // kActRopeKv (LLaMA QKV projection at prefill, N = 3 * rk_H): the epilogue rounds q | k | v to fp16, applies rotate-half
+  // RoPE to q and k (position of row m = rk_pos0 + m % rk_T), writes q to C and k / v straight into the paged KV cache
+  // [page][head][rk_page_tokens][128] of sequence m / rk_T (replaces the separate rope_kv_kernel pass: one read and one
+  // write of the whole QKV buffer per layer).  No bias / residual / row remap in this mode.
+  const float2* rk_cos_sin = nullptr;  // [position][64] (cos, sin)
+  __half* rk_k_pool = nullptr;
+  __half* rk_v_pool = nullptr;
+  const int32_t* rk_block_table = nullptr;  // [sequence][rk_max_pages]
+  int rk_T = 0, rk_pos0 = 0, rk_max_pages = 0, rk_heads = 0, rk_H = 0, rk_page_tokens = 0;
 };
 
 // A: [M,K] fp16 row-major (lda elements), W: [N,K] fp16 row-major (ldw elements). K % 64 == 0,

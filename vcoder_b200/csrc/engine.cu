@@ -783,6 +783,11 @@ int engine_prefill(Engine* e, const int64_t* ids, int B, int T, const void* imag
   const size_t layer_pool = static_cast<size_t>(e->n_pages) * c.llm_heads * c.kv_page_tokens * 128;
   __half* xn = e->xn.as<__half>();
   __half* qkv = e->qkv.as<__half>();
+  // VCB_PREFILL_ROPE=kernel: RoPE + KV append as a separate pass over the QKV buffer (rope_kv_kernel); default: fused
+  // into the QKV GEMM's epilogue (bit-identical: the epilogue rotates the fp16-rounded values)
+  static int rope_fused_env = -1;
+  if (rope_fused_env < 0) { const char* ev = getenv("VCB_PREFILL_ROPE"); rope_fused_env = (ev && ev[0] == 'k') ? 0 : 1; }
+  const bool fuse_prefill_rope = rope_fused_env != 0;
   for (int li = 0; li < c.llm_layers; ++li) {
     const LlmLayerW& l = e->llm[li];
     __half* kp = e->k_pool.as<__half>() + li * layer_pool;
@@ -791,10 +796,17 @@ int engine_prefill(Engine* e, const int64_t* ids, int B, int T, const void* imag
     {
       GemmEpilogue ep;
       ep.C = qkv; ep.ldc = 3 * H;
+      if (fuse_prefill_rope) {  // RoPE + KV append in the epilogue of the QKV GEMM (q -> qkv buffer, k / v -> page pool)
+        ep.act = kActRopeKv;
+        ep.rk_cos_sin = e->rope.as<float2>(); ep.rk_k_pool = kp; ep.rk_v_pool = vp;
+        ep.rk_block_table = e->block_table.as<int32_t>(); ep.rk_max_pages = e->max_pages_per_seq;
+        ep.rk_T = Ts; ep.rk_pos0 = L0; ep.rk_heads = c.llm_heads; ep.rk_H = H; ep.rk_page_tokens = c.kv_page_tokens;
+      }
       VCB_TRY(gemm_f16(xn, H, l.qkv_w.as<__half>(), H, rows, 3 * H, H, ep, 0, st));
     }
-    VCB_TRY(rope_kv_write(qkv, B, Ts, H, c.llm_heads, e->rope.as<float2>(), L0, nullptr, kp, vp,
-                          e->block_table.as<int32_t>(), e->max_pages_per_seq, c.kv_page_tokens, st));
+    if (!fuse_prefill_rope)
+      VCB_TRY(rope_kv_write(qkv, B, Ts, H, c.llm_heads, e->rope.as<float2>(), L0, nullptr, kp, vp,
+                            e->block_table.as<int32_t>(), e->max_pages_per_seq, c.kv_page_tokens, st));
     {
       AttnPrefillParams a;
       a.q = qkv; a.q_stride = 3 * H;

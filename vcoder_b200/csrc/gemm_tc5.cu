@@ -72,6 +72,60 @@ __device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, 
 template <int BN, int ACT>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpilogue& ep, uint32_t tmem_acc, int m, int M, int N, int n_base) {
   const bool row_ok = m < M;
+  if (ACT == kActRopeKv) {
+    // q | k | v of one token row, one 128-column head at a time: columns d and d + 64 of a head rotate together
+    // (apply_rotary_pos_emb, modeling_llama.py:124-168; same arithmetic on the fp16-rounded values as rope_kv_kernel)
+    int page = 0, slot = 0;
+    const float2* csr = ep.rk_cos_sin;
+    if (row_ok) {
+      const int b = m / ep.rk_T, pos = ep.rk_pos0 + (m - b * ep.rk_T);
+      page = ep.rk_block_table[b * ep.rk_max_pages + pos / ep.rk_page_tokens];
+      slot = pos % ep.rk_page_tokens;
+      csr += static_cast<long>(pos) * 64;
+    }
+#pragma unroll 1
+    for (int hb = 0; hb < BN; hb += 128) {
+      const int n0 = n_base + hb;
+      if (n0 >= N) break;
+      const int sect = n0 / ep.rk_H;  // 0 = q, 1 = k, 2 = v (H is a multiple of the tile width)
+      const int head = (n0 - sect * ep.rk_H) >> 7;
+      __half* dst;
+      if (sect == 0) dst = ep.C + static_cast<long>(m) * ep.ldc + n0;
+      else dst = (sect == 1 ? ep.rk_k_pool : ep.rk_v_pool) +
+                 ((static_cast<long>(page) * ep.rk_heads + head) * ep.rk_page_tokens + slot) * 128;
+#pragma unroll 1
+      for (int cc = 0; cc < 64; cc += 32) {
+        uint32_t lo[32], hi[32];
+        tmem_ld_32x32(tmem_acc + hb + cc, lo);
+        tmem_ld_32x32(tmem_acc + hb + 64 + cc, hi);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float o1[8], o2[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float x1 = __half2float(__float2half_rn(__uint_as_float(lo[j + e])));
+              const float x2 = __half2float(__float2half_rn(__uint_as_float(hi[j + e])));
+              if (sect < 2) {
+                const float2 cs = __ldg(csr + cc + j + e);
+                o1[e] = x1 * cs.x - x2 * cs.y;
+                o2[e] = x2 * cs.x + x1 * cs.y;
+              } else {
+                o1[e] = x1;
+                o2[e] = x2;
+              }
+            }
+            *reinterpret_cast<uint4*>(dst + cc + j) =
+                make_uint4(pack_half2(o1[0], o1[1]), pack_half2(o1[2], o1[3]), pack_half2(o1[4], o1[5]), pack_half2(o1[6], o1[7]));
+            *reinterpret_cast<uint4*>(dst + 64 + cc + j) =
+                make_uint4(pack_half2(o2[0], o2[1]), pack_half2(o2[2], o2[3]), pack_half2(o2[4], o2[5]), pack_half2(o2[6], o2[7]));
+          }
+        }
+      }
+    }
+    return;
+  }
   long out_row = m;
   if (ep.out_group) out_row = m + static_cast<long>(m / ep.out_group) * ep.out_skip + ep.out_off;
   const long res_row = ep.res_mod ? static_cast<long>(m % ep.res_mod) + ep.res_off : out_row;
@@ -485,6 +539,7 @@ int launch_act(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpilogu
     case kActQuickGelu: return launch<BN, kActQuickGelu>(tmA, tmB, ep, M, N, K, stream);
     case kActGeluErf: return launch<BN, kActGeluErf>(tmA, tmB, ep, M, N, K, stream);
     case kActSwiGLU: return launch<BN, kActSwiGLU>(tmA, tmB, ep, M, N, K, stream);
+    case kActRopeKv: return launch<BN, kActRopeKv>(tmA, tmB, ep, M, N, K, stream);
     default: set_thread_error("gemm_f16: unknown activation"); return kErrInvalid;
   }
 }
@@ -525,6 +580,7 @@ int launch_pair_act(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEp
     case kActQuickGelu: return launch_pair<kActQuickGelu>(tmA, tmB, ep, M, N, K, stream);
     case kActGeluErf: return launch_pair<kActGeluErf>(tmA, tmB, ep, M, N, K, stream);
     case kActSwiGLU: return launch_pair<kActSwiGLU>(tmA, tmB, ep, M, N, K, stream);
+    case kActRopeKv: return launch_pair<kActRopeKv>(tmA, tmB, ep, M, N, K, stream);
     default: set_thread_error("gemm_f16: unknown activation"); return kErrInvalid;
   }
 }
@@ -618,6 +674,14 @@ int gemm_f16(const __half* A, int lda, const __half* W, int ldw, int M, int N, i
                 (reinterpret_cast<uintptr_t>(ep.C) & 15) == 0,
             kErrInvalid, "gemm_f16: pointers must be 16-byte aligned");
   VCB_CHECK(ep.C != nullptr && ep.ldc % 8 == 0, kErrInvalid, "gemm_f16: bad output");
+  if (ep.act == kActRopeKv) {
+    VCB_CHECK(ep.rk_cos_sin && ep.rk_k_pool && ep.rk_v_pool && ep.rk_block_table && ep.rk_T > 0 && ep.rk_page_tokens > 0 &&
+                  ep.rk_H == ep.rk_heads * 128 && N == 3 * ep.rk_H && M % ep.rk_T == 0,
+              kErrInvalid, "gemm_f16: incomplete RoPE / KV-append epilogue description");
+    VCB_CHECK(ep.bias == nullptr && ep.residual == nullptr && ep.out_group == 0, kErrInvalid,
+              "gemm_f16: the RoPE / KV-append epilogue takes no bias, residual or row remap");
+    if (ep.rk_H % 256 != 0) block_n = 128;  // a tile must not straddle q | k | v
+  }
   {
     // block_n == 512 or VCB_GEMM_PAIR=1: CTA-pair kernel (256 x 256 tile per two SMs) where the shape allows it
     static int env_pair = -1;
