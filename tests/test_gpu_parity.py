@@ -454,3 +454,55 @@ torch.save({"dec": dec.cpu(), "lg": lg.float().cpu(), "gen": gen.cpu()}, sys.arg
     for s in range(a["dec"].shape[1]):
         assert bool((same[s] | ~alive | (margin[s] <= 4e-2)).all()), (s, a["dec"][:, s], b["dec"][:, s])
         alive &= same[s]
+
+
+@pytest.mark.gpu
+def test_prefill_rope_epilogue_bit_identical_to_separate_pass():
+    """RoPE + KV append in the QKV GEMM epilogue (default) vs the separate rope_kv_kernel pass (VCB_PREFILL_ROPE=kernel):
+    the epilogue rotates the fp16-ROUNDED q / k with the same expression, so logits, cache contents (seen through the
+    decode steps and a prefix-cached second prefill) and ids are bit-identical — at the tiny geometry (BN = 128 tiles,
+    1-CTA kernel) and at the 7B width (256 x 256 CTA-pair tiles, two heads per tile)."""
+    import subprocess, sys, tempfile
+    code = r'''
+import sys, dataclasses, torch
+sys.path.insert(0, %r)
+from vcoder_b200 import synth
+from vcoder_b200.engine import Engine
+out = {}
+# tiny geometry, multimodal prompt, then a second turn that reuses the KV prefix (q_pos0 > 0 in the epilogue)
+g = synth.PRESETS["tiny"].with_variant(synth.VARIANT_VCODER_DS)
+eng = Engine(g, max_batch=2, max_seq_len=192)
+eng.bind(synth.make_state_dict(g, seed=0))
+ids = synth.make_prompt_ids(g, 2, seed=4, n_before=6, n_after=5)
+px = [synth.make_pixels(g, 2, s) for s in (1, 2, 3)]
+pre = eng.prefill(ids, *px, want_logits=True)
+dec, lg = eng.decode(5, want_logits=True)
+out["tiny_pre"], out["tiny_dec"], out["tiny_lg"] = pre["logits"].cpu(), dec.cpu(), lg.cpu()
+ids2 = torch.cat([ids, dec[:, :3].cpu().long(), torch.full((2, 4), 17)], dim=1)
+pre2 = eng.prefill(ids2, *px, want_logits=True, reuse=True)
+out["tiny_reused"], out["tiny_pre2"] = int(pre2["reused_len"]), pre2["logits"].cpu()
+eng.close()
+# 7B width behind the tiny tower, two layers, text-only prompt of 300 tokens (more than two 128-row tiles per sequence)
+g7 = dataclasses.replace(synth.PRESETS["tiny"], name="tiny-vit+7b", llm_hidden=4096, llm_heads=32, llm_ffn=11008, llm_layers=2,
+                         llm_vocab=32000, init_gain=1.0)
+eng = Engine(g7, max_batch=2, max_seq_len=384)
+eng.bind(synth.make_state_dict(g7, seed=1))
+t_ids = torch.randint(3, g7.llm_vocab, (2, 300), generator=torch.Generator().manual_seed(5))
+pre = eng.prefill(t_ids, want_logits=True)
+dec, lg = eng.decode(4, want_logits=True)
+out["w7_pre"], out["w7_dec"], out["w7_lg"] = pre["logits"].cpu(), dec.cpu(), lg.cpu()
+eng.close()
+torch.save(out, sys.argv[1])
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for mode in ("kernel", "fused"):
+        with tempfile.NamedTemporaryFile(suffix=".pt") as f:
+            env = dict(os.environ, VCB_PREFILL_ROPE=mode)
+            r = subprocess.run([sys.executable, "-c", code, f.name], env=env, capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, r.stderr[-2000:]
+            outs[mode] = torch.load(f.name)
+    a, b = outs["kernel"], outs["fused"]
+    assert a["tiny_reused"] == b["tiny_reused"] and a["tiny_reused"] > 0
+    for k in a:
+        if k != "tiny_reused":
+            assert torch.equal(a[k], b[k]), k
