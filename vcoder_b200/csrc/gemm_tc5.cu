@@ -10,7 +10,7 @@
 // Structure (persistent, warp-specialised, one CTA per SM, 192 threads):
 //   warp 0 / lane 0 : TMA producer  — cp.async.bulk.tensor 128B-swizzled K-major tiles of A (128x64) and W (BNx64)
 //   warp 1 / lane 0 : MMA issuer    — 4 x tcgen05.mma (128 x BN x 16) per k-block, accumulators double-buffered in TMEM
-//   warps 2..5      : epilogue      — tcgen05.ld TMEM -> registers, bias / activation / residual, fp16 stores
+//   warps 2..9      : epilogue      — tcgen05.ld TMEM -> registers, bias / activation / residual, fp16 stores
 // Three mbarrier pipelines: smem full/empty (TMA<->MMA), TMEM full/empty (MMA<->epilogue), static tile round-robin.
 #include <algorithm>
 #include <cstdlib>
@@ -26,7 +26,7 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 fp16 = 128 bytes = one swizzle-128B row
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps (two per TMEM lane quadrant, half of the tile's columns each)
 constexpr int kRasterGroup1 = 16;  // tile rows per band, 1-CTA kernel: minimises 16 x 1 MB (A) + 148/16 x 2 MB (W) per wave at K = 4096
 constexpr int kRasterGroup2 = 8;   // CTA-pair kernel: 8 x 2 MB + 74/8 x 2 MB
 constexpr int kGemmPairDefault = 1;  // VCB_GEMM_PAIR=0 forces the 1-CTA kernel (A/B: DESIGN.md section 3, profiles/r01_gemm_pair_s3.log)
@@ -69,8 +69,12 @@ __device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, 
 // Epilogue of one accumulator row: `tmem_acc` = TMEM address of this thread's lane at the first column of the accumulator
 // buffer, m = global output row, n_base = first global column of the tile.  tcgen05.ld -> bias / activation / residual ->
 // fp16 stores (a thread owns one row, 32 columns at a time).
+// [c_begin, c_end): the columns of the tile this warp handles.  Two warps share a lane quadrant: with a 16-k-block mainloop
+// (the K = 1024 tower GEMMs) four epilogue warps needed ~12.7 k cycles per 128 x 256 tile against 8.2 k of MMAs and held the
+// tensor pipe at 64 % (profiles/r02_ncu_gemm_tower_vs_prefill_s2.csv).
 template <int BN, int ACT>
-__device__ __forceinline__ void gemm_epilogue_tile(const GemmEpilogue& ep, uint32_t tmem_acc, int m, int M, int N, int n_base) {
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmEpilogue& ep, uint32_t tmem_acc, int m, int M, int N, int n_base,
+                                                   int c_begin, int c_end) {
   const bool row_ok = m < M;
   if (ACT == kActRopeKv) {
     // q | k | v of one token row, one 128-column head at a time: columns d and d + 64 of a head rotate together
@@ -84,7 +88,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpilogue& ep, uint3
       csr += static_cast<long>(pos) * 64;
     }
 #pragma unroll 1
-    for (int hb = 0; hb < BN; hb += 128) {
+    for (int hb = c_begin; hb < c_end; hb += 128) {
       const int n0 = n_base + hb;
       if (n0 >= N) break;
       const int sect = n0 / ep.rk_H;  // 0 = q, 1 = k, 2 = v (H is a multiple of the tile width)
@@ -130,7 +134,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpilogue& ep, uint3
   if (ep.out_group) out_row = m + static_cast<long>(m / ep.out_group) * ep.out_skip + ep.out_off;
   const long res_row = ep.res_mod ? static_cast<long>(m % ep.res_mod) + ep.res_off : out_row;
 #pragma unroll 1
-  for (int c = 0; c < BN; c += 32) {
+  for (int c = c_begin; c < c_end; c += 32) {
     const int n0 = n_base + c;
     if (n0 >= N) break;
     uint32_t r[32];
@@ -207,8 +211,8 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int i = 0; i < 2 * S; ++i) mbar_init(bar(i), 1);
     mbar_init(bar(2 * S + 0), 1);
     mbar_init(bar(2 * S + 1), 1);
-    mbar_init(bar(2 * S + 2), 4);
-    mbar_init(bar(2 * S + 3), 4);
+    mbar_init(bar(2 * S + 2), 8);
+    mbar_init(bar(2 * S + 3), 8);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -272,8 +276,12 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else {
-    // ---------------------------------------------------------------- epilogue warps 2..5
+    // ---------------------------------------------------------------- epilogue warps 2..9
     const int q = warp & 3;  // a warp may only touch TMEM lanes [32*(warpid%4), +32)
+    // column half of this warp; the RoPE epilogue keeps the 128 columns of a head together (BN = 128: one warp per quadrant)
+    const int half = (warp - 2) >> 2;
+    const int c_begin = (ACT == kActRopeKv && BN == 128) ? (half == 0 ? 0 : BN) : half * (BN / 2);
+    const int c_end = (ACT == kActRopeKv && BN == 128) ? BN : (half + 1) * (BN / 2);
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -283,7 +291,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(bar(2 * S + acc), acc_phase);
       tc_fence_after();
       gemm_epilogue_tile<BN, ACT>(ep, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN, tm * BM + q * 32 + lane, M, N,
-                                  tn * BN);
+                                  tn * BN, c_begin, c_end);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(2 * S + 2 + acc));
@@ -310,7 +318,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 //                loads complete_tx on it (tma_load_2d_2sm)
 //   empty[s]     (each CTA, count 1): tcgen05.commit multicast from the leader's MMA thread
 //   tmem_full[a] (each CTA, count 1): commit multicast after the tile's last k-block
-//   tmem_empty[a](leader only, count 8): the four epilogue warps of each CTA (the peer's arrive through DSMEM)
+//   tmem_empty[a](leader only, count 16): the eight epilogue warps of each CTA (the peer's arrive through DSMEM)
 // -------------------------------------------------------------------------------------------------
 struct PairCfg {
   static constexpr int kStages = 6;
@@ -346,8 +354,8 @@ gemm_tc5_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     for (int i = 0; i < 2 * S; ++i) mbar_init(bar(i), 1);
     mbar_init(bar(2 * S + 0), 1);
     mbar_init(bar(2 * S + 1), 1);
-    mbar_init(bar(2 * S + 2), 8);
-    mbar_init(bar(2 * S + 3), 8);
+    mbar_init(bar(2 * S + 2), 16);
+    mbar_init(bar(2 * S + 3), 16);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -410,6 +418,8 @@ gemm_tc5_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
   } else {
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;  // two epilogue warps per lane quadrant: 128 of the 256 columns each (one head for RoPE)
+    const int c_begin = half * (BN / 2), c_end = (half + 1) * (BN / 2);
     int it = 0;
     for (int tile = pair; tile < num_tiles; tile += n_pairs, ++it) {
       const int acc = it & 1;
@@ -419,7 +429,7 @@ gemm_tc5_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       mbar_wait(bar(2 * S + acc), acc_phase);
       tc_fence_after();
       gemm_epilogue_tile<BN, ACT>(ep, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN,
-                                  tm * 256 + static_cast<int>(rank) * BM + q * 32 + lane, M, N, tn * BN);
+                                  tm * 256 + static_cast<int>(rank) * BM + q * 32 + lane, M, N, tn * BN, c_begin, c_end);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
