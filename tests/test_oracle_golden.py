@@ -12,12 +12,15 @@ from vcoder_b200 import synth
 
 CASES = [("tiny_ds.npz", synth.VARIANT_VCODER_DS), ("tiny_vcoder.npz", synth.VARIANT_VCODER),
          # plain LLaVA-1.5 (llava_arch.py) and VCoder-IT (vcoder_it_llava_arch.py), same generator script
-         ("tiny_llava.npz", synth.VARIANT_LLAVA), ("tiny_it.npz", synth.VARIANT_VCODER_IT)]
+         ("tiny_llava.npz", synth.VARIANT_LLAVA), ("tiny_it.npz", synth.VARIANT_VCODER_IT),
+         # a second geometry (synth.PRESETS["small"]: 65 ViT tokens, 4 heads, 6 + 3 layers, FFN 640 / 1408), written by the
+         # reference with `tools/make_golden.py --small`: the oracle is not only pinned at the tiny shape
+         ("small_ds.npz", synth.VARIANT_VCODER_DS)]
 
 
 def _load(golden_dir, fname, variant):
     z = np.load(os.path.join(golden_dir, fname))
-    g = synth.PRESETS["tiny"].with_variant(variant)
+    g = synth.PRESETS[fname.split("_")[0]].with_variant(variant)  # tiny_*.npz / small_*.npz
     sd = synth.make_state_dict(g, seed=0)
     assert synth.state_dict_digest(sd) == str(z["weights_digest"]), "seeded weight generator drifted from the fixture"
     B = z["ids"].shape[0]

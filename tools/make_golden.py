@@ -263,6 +263,9 @@ if __name__ == "__main__":
     if "--multi-turn" in sys.argv:  # f3 fixture alone (the others stay byte-identical)
         multi_turn_fixture(synth.PRESETS["tiny"].with_variant(synth.VARIANT_VCODER_DS), os.path.join(gold, "tiny_ds_turn2.npz"))
         sys.exit(0)
+    if "--small" in sys.argv:  # second pinning geometry alone (the tiny fixtures stay byte-identical)
+        run_variant(synth.PRESETS["small"].with_variant(synth.VARIANT_VCODER_DS), os.path.join(gold, "small_ds.npz"), batch=1, n_new=5)
+        sys.exit(0)
     only_new = "--only-new" in sys.argv  # keep the committed a-row fixtures byte-identical
     if not only_new:
         run_variant(synth.PRESETS["tiny"].with_variant(synth.VARIANT_VCODER_DS), os.path.join(gold, "tiny_ds.npz"))

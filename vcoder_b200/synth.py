@@ -5,6 +5,7 @@ dict feeds (a) the reference itself (``load_state_dict`` in tools/make_golden.py
 
 Geometry presets:
   tiny     – fast CI / golden fixtures (CLIP hidden 128, 4 layers, 56 px; LLaMA hidden 256, 2 layers, vocab 512)
+  small    – second golden geometry (CLIP hidden 256, 6 layers, 112 px = 65 tokens; LLaMA hidden 512, 3 layers)
   vit_l    – real CLIP ViT-L/14@336 tower with a 2-layer LLaMA-7B-shaped decoder (mid-size parity on the GPU box)
   7b / 13b – VCoder(-DS) LLaVA-1.5-7B / 13B (BASELINE.json configs 2-4)
 """
@@ -70,6 +71,11 @@ PRESETS: Dict[str, ModelGeometry] = {
     "tiny": ModelGeometry(
         name="tiny", vit_image_size=56, vit_hidden=128, vit_heads=2, vit_ffn=256, vit_layers=4,
         llm_hidden=256, llm_layers=2, llm_heads=2, llm_ffn=512, llm_vocab=512, init_gain=3.0),
+    # second pinning geometry of the oracle (tests/golden/small_ds.npz): 64 patches + CLS = 65 tokens (S % 64 == 1 like the
+    # real tower's 577), head counts > 2, more layers than `tiny`, FFN not a power of two
+    "small": ModelGeometry(
+        name="small", vit_image_size=112, vit_hidden=256, vit_heads=4, vit_ffn=640, vit_layers=6,
+        llm_hidden=512, llm_layers=3, llm_heads=4, llm_ffn=1408, llm_vocab=512, init_gain=3.0),
     "vit_l": ModelGeometry(name="vit_l", llm_layers=2),
     "7b": ModelGeometry(name="7b"),
     "13b": ModelGeometry(name="13b", llm_hidden=5120, llm_layers=40, llm_heads=40, llm_ffn=13824),
