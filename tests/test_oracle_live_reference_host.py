@@ -1,7 +1,8 @@
 """The CPU oracle against THE REFERENCE ITSELF at the real widths (CPU, this container only): the real CLIP ViT-L/14@336
 tower (24 layers, 577 tokens) and a LLaMA-7B-width decoder cut to one layer, VCoder-DS, one sample — the geometry the
 committed fixtures (tiny / small, tests/golden/) cannot carry (a real-size fixture is hundreds of MB).  Runs the reference's
-CLIPVisionTower / encode_* / prepare_inputs_labels_for_multimodal / model + lm_head (through tools/make_golden.py's builder)
+CLIPVisionTower / encode_* / prepare_inputs_labels_for_multimodal / model + lm_head incl. three cached greedy steps (through
+tools/make_golden.py's builder)
 and the oracle on the same seeded weights in a child process (the reference import patches transformers' registries), and
 compares fp32 with fp32.
 
@@ -49,6 +50,17 @@ with tempfile.TemporaryDirectory() as td:
     logits = logits[0] if isinstance(logits, tuple) else logits
     out["last_logits"] = rel(logits.reshape(ref_logits.shape), ref_logits)
     out["argmax_equal"] = bool(torch.equal(logits.reshape(ref_logits.shape).argmax(-1), ref_logits.argmax(-1)))
+    # greedy decode with the KV cache, route (ii) of SURVEY 8(c): three tokens from the reference's own modules
+    o = m.model(inputs_embeds=embeds, use_cache=True)
+    past, lg = o.past_key_values, m.lm_head(o.last_hidden_state)[:, -1]
+    ref_ids, ref_steps = [lg.argmax(-1)], [lg]
+    for _ in range(2):
+        o = m.model(input_ids=ref_ids[-1][:, None], past_key_values=past, use_cache=True)
+        past, lg = o.past_key_values, m.lm_head(o.last_hidden_state)[:, -1]
+        ref_ids.append(lg.argmax(-1)); ref_steps.append(lg)
+    got_ids, got_steps = orc.greedy_generate(ids, sd, g, *px, max_new_tokens=3, return_logits=True)
+    out["greedy_equal"] = bool(torch.equal(got_ids, torch.stack(ref_ids, dim=1)))
+    out["decode_logits"] = max(rel(a.reshape(b.shape), b) for a, b in zip(got_steps, ref_steps))
 print("RESULT " + json.dumps(out))
 '''
 
@@ -63,4 +75,4 @@ def test_oracle_matches_the_live_reference_at_real_vit_l_and_7b_width():
     # fp32 against fp32: summation order only
     for k in ("tower", "image_features", "seg_features", "depth_features", "inputs_embeds", "last_logits"):
         assert out[k] <= 2e-4, (k, out)
-    assert out["argmax_equal"]
+    assert out["argmax_equal"] and out["greedy_equal"] and out["decode_logits"] <= 2e-4, out
