@@ -28,7 +28,7 @@ import make_golden as mg            # inserts the reference into sys.path and ap
 from oracle import vcoder_oracle as orc
 from vcoder_b200 import synth
 torch.set_grad_enabled(False)
-g = dataclasses.replace(synth.PRESETS["7b"], llm_layers=1).with_variant(synth.VARIANT_VCODER_DS)
+g = (%(geom)s).with_variant(synth.VARIANT_VCODER_DS)
 sd = synth.make_state_dict(g, seed=0)
 ids = synth.make_prompt_ids(g, 1, seed=0, n_before=5, n_after=4)
 px = [synth.make_pixels(g, 1, s).float() for s in (1, 2, 3)]
@@ -65,13 +65,24 @@ print("RESULT " + json.dumps(out))
 '''
 
 
-def test_oracle_matches_the_live_reference_at_real_vit_l_and_7b_width():
-    r = subprocess.run([sys.executable, "-c", CODE % {"root": ROOT}], capture_output=True, text=True, timeout=900,
+GEOMETRIES = {
+    # the real CLIP ViT-L/14@336 tower + one LLaMA-7B-width decoder layer
+    "vit_l+7b": ('dataclasses.replace(synth.PRESETS["7b"], llm_layers=1)', 576),
+    # configs[3]'s decoder width (13B: hidden 5120, 40 heads, FFN 13824) behind the tiny tower
+    "tiny_vit+13b": ('dataclasses.replace(synth.PRESETS["tiny"], llm_hidden=5120, llm_heads=40, llm_ffn=13824, llm_layers=1, '
+                     'llm_vocab=32000, init_gain=1.0)', 16),
+}
+
+
+@pytest.mark.parametrize("name", sorted(GEOMETRIES))
+def test_oracle_matches_the_live_reference_at_real_widths(name):
+    geom, n_patches = GEOMETRIES[name]
+    r = subprocess.run([sys.executable, "-c", CODE % {"root": ROOT, "geom": geom}], capture_output=True, text=True, timeout=900,
                        env=dict(os.environ, PYTHONDONTWRITEBYTECODE="1"))
     assert r.returncode == 0, r.stderr[-3000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1]
     out = json.loads(line[len("RESULT "):])
-    assert out["spliced_len"][0] == out["spliced_len"][1] == out["spliced_len"][2] - 3 + 2 * 576  # depth computed, then dropped (F5)
+    assert out["spliced_len"][0] == out["spliced_len"][1] == out["spliced_len"][2] - 3 + 2 * n_patches  # depth computed, then dropped (F5)
     # fp32 against fp32: summation order only
     for k in ("tower", "image_features", "seg_features", "depth_features", "inputs_embeds", "last_logits"):
         assert out[k] <= 2e-4, (k, out)
